@@ -1,0 +1,101 @@
+/* pfb_b200.h — C ABI of the B200-native oversampled PFB analysis / inversion.
+ *
+ * This is the drop-in boundary for the hot path of ska-telescope/ska-pst-dsp-model.
+ * The reference has no FFI of its own (its "native" side is Matlab compiled by
+ * mcc and a third-party numpy package), so each entry point below names the
+ * reference interface it replaces; INTEGRATION.md shows the ctypes binding the
+ * reference's python/data_gen would add.
+ *
+ * Conventions
+ *  - every function returns 0 on success or a negative PFB_ERR_* code;
+ *    pfb_last_error() returns a thread-local message for the last failure.
+ *  - all data pointers are DEVICE pointers owned by the caller (e.g. a torch
+ *    tensor's data_ptr()); plans own only their tables and scratch.
+ *  - data layout is the DADA "TFP" order of the reference files
+ *    (matlab/write_dada_data.m:32-50): time slowest, then channel, then
+ *    polarisation, interleaved (re,im); dtype 0 = complex64, 1 = complex128.
+ *  - calls are stream-ordered on `stream` (a cudaStream_t cast to void*; NULL =
+ *    legacy default stream); one plan must not be used from two streams at once.
+ */
+#ifndef PFB_B200_H
+#define PFB_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PFB_OK 0
+#define PFB_ERR_ARG (-1)         /* invalid argument / unsupported shape */
+#define PFB_ERR_CUDA (-2)        /* CUDA runtime error (see pfb_last_error) */
+#define PFB_ERR_UNSUPPORTED (-3) /* valid in the reference but not implemented here */
+
+#define PFB_DTYPE_C64 0
+#define PFB_DTYPE_C128 1
+
+/* analysis variants == config "analysis_function" (config/test.config.json) */
+#define PFB_VARIANT_BUNTON 0 /* matlab/polyphase_analysis.m        */
+#define PFB_VARIANT_PADDED 1 /* matlab/polyphase_analysis_padded.m */
+#define PFB_VARIANT_LOWCBF 2 /* matlab/polyphase_analysis_lowcbf.m + PSTFilterbank.m */
+
+typedef struct pfb_analysis_plan pfb_analysis_plan;
+typedef struct pfb_inverse_plan pfb_inverse_plan;
+
+const char* pfb_last_error(void);
+int pfb_version(void);
+
+/* ---- analysis: replaces out = polyphase_analysis[_padded|_lowcbf](in, filt, block, os_factor)
+ *      (matlab/polyphase_analysis.m:1-7, FilterBank.m:91 plugin slot) and the
+ *      pfb.format_handler.PSRFormatChannelizer call of python/data_gen/channelize.py:81-91.
+ *      taps: ntaps doubles exactly as read from the coefficient file (padding,
+ *      reversal and precision cast happen inside). */
+int pfb_analysis_plan_create(pfb_analysis_plan** plan, int variant, int nchan, int os_nu, int os_de,
+                             const double* taps, int ntaps, int dtype, int device);
+int pfb_analysis_plan_destroy(pfb_analysis_plan* plan);
+/* number of output time samples ("nblocks", polyphase_analysis.m:62 / _padded.m:75 /
+ * PSTFilterbank.m:15) for n_dat input samples; first_call models the persistent
+ * pre-padding flag of polyphase_analysis_lowcbf.m:27-34 (ignored otherwise). */
+long long pfb_analysis_nblocks(const pfb_analysis_plan* plan, long long n_dat, int first_call);
+int pfb_analysis_nchan_out(const pfb_analysis_plan* plan); /* block, or 216 for lowcbf */
+/* in: [n_dat][npol]; out: [nblocks][nchan_out][npol] */
+int pfb_analysis_execute(pfb_analysis_plan* plan, const void* in_dev, void* out_dev, int npol,
+                         long long n_dat, int first_call, void* stream);
+/* Time-segment form (multi-GPU sharding / streaming, cf. FilterBank.m:85-88,119-126):
+ * compute output blocks [k_first, k_first+nblk) of the stream. in_dev[0] is absolute
+ * stream sample `sample0`, n_local samples are resident; samples outside read as 0.
+ * out_dev[0] is block k_first.  Bunton and lowcbf variants only. */
+int pfb_analysis_execute_segment(pfb_analysis_plan* plan, const void* in_dev, long long n_local,
+                                 long long sample0, void* out_dev, int npol, long long k_first,
+                                 long long nblk, int first_call, void* stream);
+
+/* ---- inversion: replaces out = polyphase_synthesis(in, spans_nyquist, input_fft_length,
+ *      os_factor, deripple, sample_offset, input_overlap, temporal_taper, spectral_taper,
+ *      combine) (matlab/polyphase_synthesis.m:1-13) and the PSRFormatSynthesizer call of
+ *      python/data_gen/synthesize.py:84-95.
+ *      temporal_taper: nfft doubles (the window itself, PFBWindow.m) or NULL;
+ *      deripple_taps: the analysis filter (n_deripple_taps > 0 applies the
+ *      polyphase_synthesis.m:138-150,242-251 correction) or NULL/0;
+ *      sample_offset is applied by the caller as a pointer offset. */
+int pfb_inverse_plan_create(pfb_inverse_plan** plan, int nchan, int os_nu, int os_de, int nfft,
+                            int overlap, const double* temporal_taper, const double* deripple_taps,
+                            int n_deripple_taps, int spans_nyquist, int combine, int dtype, int device);
+int pfb_inverse_plan_destroy(pfb_inverse_plan* plan);
+long long pfb_inverse_nblocks(const pfb_inverse_plan* plan, long long n_dat);
+long long pfb_inverse_out_len(const pfb_inverse_plan* plan, long long n_dat); /* n_blocks*output_keep */
+/* in: [n_dat][nchan][npol]; out: [out_len][npol] */
+int pfb_inverse_execute(pfb_inverse_plan* plan, const void* in_dev, void* out_dev, int npol,
+                        long long n_dat, void* stream);
+/* bytes of L2-resident scratch used between the two inversion kernels (default 32 MiB) */
+int pfb_inverse_set_scratch_bytes(pfb_inverse_plan* plan, long long bytes);
+/* run only one stage of the chain over the whole input (profiling / roofline):
+ * stage 0 = channel IDFT into the caller's v buffer [n_dat][nchan][npol],
+ * stage 1 = overlap-save resampling from such a v buffer. */
+int pfb_inverse_execute_stage(pfb_inverse_plan* plan, int stage, const void* in_dev, void* out_dev,
+                              int npol, long long n_dat, void* stream);
+
+/* kernels launched by this library since load (bench.py "gpu_launches") */
+long long pfb_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PFB_B200_H */

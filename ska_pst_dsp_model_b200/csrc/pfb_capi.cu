@@ -1,0 +1,547 @@
+// C ABI (include/pfb_b200.h) + host-side plan construction for the B200 PFB
+// analysis / inversion kernels.  Build:
+//   nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/pfb_b200.h"
+#include "pfb_generic.cuh"
+#include "pfb_low.cuh"
+
+using namespace pfb;
+
+namespace {
+
+thread_local std::string g_err;
+std::atomic<long long> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define CU(call)                                                                              \
+  do {                                                                                        \
+    cudaError_t e_ = (call);                                                                  \
+    if (e_ != cudaSuccess) return fail(PFB_ERR_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+const double kPi = 3.14159265358979323846264338327950288;
+
+struct DeviceTables {
+  std::vector<void*> ptrs;
+  ~DeviceTables() {
+    for (void* p : ptrs) cudaFree(p);
+  }
+  template <typename U> int upload(const std::vector<U>& h, const U** out) {
+    void* d = nullptr;
+    CU(cudaMalloc(&d, h.size() * sizeof(U) + 16));
+    ptrs.push_back(d);
+    CU(cudaMemcpy(d, h.data(), h.size() * sizeof(U), cudaMemcpyHostToDevice));
+    *out = reinterpret_cast<const U*>(d);
+    return PFB_OK;
+  }
+};
+
+// exact-as-possible unit-circle point exp(sign * 2 pi i m / n)
+void unit(long long m, long long n, int sign, double* c, double* s) {
+  m %= n;
+  if (m < 0) m += n;
+  const double a = 2.0 * kPi * ((double)m / (double)n);
+  *c = cos(a);
+  *s = sign * sin(a);
+  if (4 * m == n) { *c = 0; *s = sign; }
+  else if (2 * m == n) { *c = -1; *s = 0; }
+  else if (4 * m == 3 * n) { *c = 0; *s = -sign; }
+  else if (m == 0) { *c = 1; *s = 0; }
+}
+
+int factorize(int n, std::vector<int>& radix) {
+  radix.clear();
+  if (n < 1) return PFB_ERR_ARG;
+  int m = n;
+  const int odd[3] = {7, 5, 3};
+  for (int p : odd)
+    while (m % p == 0) { radix.push_back(p); m /= p; }
+  int e = 0;
+  while (m % 2 == 0) { m /= 2; ++e; }
+  if (m != 1) return PFB_ERR_ARG;
+  if (e % 3 == 1) radix.push_back(2);
+  if (e % 3 == 2) radix.push_back(4);
+  for (int i = 0; i < e / 3; ++i) radix.push_back(8);
+  if (radix.empty()) radix.push_back(1);
+  if ((int)radix.size() > kMaxPass) return PFB_ERR_ARG;
+  return PFB_OK;
+}
+
+template <typename T> int build_fft(int n, FftDev* dev, DeviceTables* tabs) {
+  std::vector<int> radix;
+  if (factorize(n, radix) != PFB_OK) return fail(PFB_ERR_ARG, "FFT length %d is not of the form 2^a 3^b 5^c 7^d", n);
+  dev->n = n;
+  if (n == 1) { dev->npass = 0; }
+  else {
+    dev->npass = (int)radix.size();
+    for (int i = 0; i < dev->npass; ++i) dev->radix[i] = radix[i];
+  }
+  std::vector<Cx<T>> tw(n);
+  for (int k = 0; k < n; ++k) {
+    double c, s;
+    unit(k, n, -1, &c, &s);
+    tw[k].x = (T)c;
+    tw[k].y = (T)s;
+  }
+  std::vector<int> perm(n);
+  for (int k = 0; k < n; ++k) {
+    int kk = k, pos = 0, stride = n;
+    for (int l = 0; l < dev->npass; ++l) {
+      const int R = dev->radix[l];
+      stride /= R;
+      pos += (kk % R) * stride;
+      kk /= R;
+    }
+    perm[k] = pos;
+  }
+  const Cx<T>* dtw;
+  const int* dperm;
+  int rc = tabs->upload(tw, &dtw);
+  if (rc) return rc;
+  rc = tabs->upload(perm, &dperm);
+  if (rc) return rc;
+  dev->tw = dtw;
+  dev->perm = dperm;
+  return PFB_OK;
+}
+
+template <typename K> int set_smem(K kernel, size_t bytes) {
+  if (bytes > 227 * 1024) return fail(PFB_ERR_ARG, "kernel needs %zu B of shared memory (> 227 KiB)", bytes);
+  CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  return PFB_OK;
+}
+
+int check_launch(const char* what) {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(PFB_ERR_CUDA, "%s launch failed: %s", what, cudaGetErrorString(e));
+  return PFB_OK;
+}
+
+}  // namespace
+
+// ===========================================================================
+struct pfb_analysis_plan {
+  int variant, N, nu, de, S, P, fl, ntaps, dtype, device;
+  int nchan_out, chan_first, sds;
+  double scale;
+  FftDev fft;
+  const void* d_taps = nullptr;     // T[fl]
+  const void* d_low_taps = nullptr; // fast Low kernel tap layout
+  bool low_fast = false;
+  DeviceTables tabs;
+};
+
+struct pfb_inverse_plan {
+  int nchan, nu, de, Nf, ov, keep, FNw, ov2, keep2, d2, off, spans, combine, dtype, device;
+  FftDev fft_chan, fft_fwd, fft_bwd;
+  const int* d_jmap = nullptr;
+  const void* d_taper = nullptr;
+  const void* d_wt = nullptr;
+  const void* d_low = nullptr;       // fast-path tables (pfb_low.cuh)
+  bool low_fast = false;
+  long long scratch_bytes = 32ll << 20;
+  void* d_scratch = nullptr;
+  size_t scratch_cap = 0;
+  DeviceTables tabs;
+  ~pfb_inverse_plan() {
+    if (d_scratch) cudaFree(d_scratch);
+  }
+};
+
+// (C linkage comes from the declarations in pfb_b200.h)
+const char* pfb_last_error(void) { return g_err.c_str(); }
+int pfb_version(void) { return 100; }
+long long pfb_launch_count(void) { return g_launches.load(); }
+
+// ---------------------------------------------------------------------------
+template <typename T> static int analysis_build(pfb_analysis_plan* p, const double* taps) {
+  int rc = build_fft<T>(p->N, &p->fft, &p->tabs);
+  if (rc) return rc;
+  std::vector<T> f(p->fl, (T)0);
+  for (int i = 0; i < p->ntaps; ++i) f[i] = (T)taps[i];
+  if (p->variant == PFB_VARIANT_PADDED) {
+    std::vector<T> r(p->fl);
+    for (int i = 0; i < p->fl; ++i) r[i] = f[p->fl - 1 - i];
+    f.swap(r);
+  }
+  const T* d;
+  rc = p->tabs.upload(f, &d);
+  if (rc) return rc;
+  p->d_taps = d;
+  return PFB_OK;
+}
+
+int pfb_analysis_plan_create(pfb_analysis_plan** plan, int variant, int nchan, int os_nu, int os_de,
+                             const double* taps, int ntaps, int dtype, int device) {
+  if (!plan || !taps || ntaps < 1 || nchan < 1 || os_nu < 1 || os_de < 1 || os_de > os_nu)
+    return fail(PFB_ERR_ARG, "pfb_analysis_plan_create: bad argument");
+  if (dtype != PFB_DTYPE_C64 && dtype != PFB_DTYPE_C128) return fail(PFB_ERR_ARG, "dtype must be 0 (c64) or 1 (c128)");
+  if (variant < 0 || variant > 2) return fail(PFB_ERR_ARG, "unknown analysis variant %d", variant);
+  CU(cudaSetDevice(device));
+  pfb_analysis_plan* p = new pfb_analysis_plan();
+  p->variant = variant; p->N = nchan; p->nu = os_nu; p->de = os_de; p->dtype = dtype; p->device = device;
+  p->ntaps = ntaps;
+  p->S = (int)(((long long)nchan * os_de) / os_nu);          // polyphase_analysis.m:56
+  p->P = (ntaps + nchan - 1) / nchan;                         // pad_filter.m:10
+  p->fl = p->P * nchan;
+  p->nchan_out = nchan; p->chan_first = 0; p->scale = nchan; p->sds = 0;
+  if (p->S < 1) { delete p; return fail(PFB_ERR_ARG, "step < 1"); }
+  if (variant == PFB_VARIANT_PADDED) {
+    p->sds = (int)std::ceil((ntaps - 1) / 2.0 / p->S);        // polyphase_analysis_padded.m:89
+  } else if (variant == PFB_VARIANT_LOWCBF) {
+    if (nchan != 256 || os_nu != 4 || os_de != 3 || ntaps != 3072) {
+      delete p;
+      return fail(PFB_ERR_ARG, "lowcbf variant is fixed at 256 channels, 4/3, 3072 taps (PSTFilterbank.m:7-16)");
+    }
+    p->nchan_out = 216; p->chan_first = 148; p->scale = 4096.0;
+  }
+  int rc = dtype == PFB_DTYPE_C64 ? analysis_build<float>(p, taps) : analysis_build<double>(p, taps);
+  if (rc == PFB_OK && variant != PFB_VARIANT_PADDED)
+    rc = low_analysis_plan_init(p->N, p->nu, p->de, p->P, p->dtype, taps, p->ntaps, &p->tabs.ptrs, &p->d_low_taps, &p->low_fast);
+  if (rc) { delete p; return rc; }
+  *plan = p;
+  return PFB_OK;
+}
+
+int pfb_analysis_plan_destroy(pfb_analysis_plan* plan) {
+  if (plan) { cudaSetDevice(plan->device); delete plan; }
+  return PFB_OK;
+}
+
+long long pfb_analysis_nblocks(const pfb_analysis_plan* p, long long n_dat, int first_call) {
+  if (!p) return PFB_ERR_ARG;
+  long long nb;
+  if (p->variant == PFB_VARIANT_PADDED) nb = n_dat / p->S;
+  else if (p->variant == PFB_VARIANT_LOWCBF) nb = (n_dat + (first_call ? 1536 : 0) - p->fl) / p->S;
+  else nb = (n_dat - p->fl) / p->S;
+  if (n_dat + (first_call ? 1536 : 0) < p->fl && p->variant != PFB_VARIANT_PADDED) nb = 0;
+  return nb < 0 ? 0 : nb;
+}
+
+int pfb_analysis_nchan_out(const pfb_analysis_plan* p) { return p ? p->nchan_out : PFB_ERR_ARG; }
+
+template <typename T> static int analysis_launch(pfb_analysis_plan* p, AnalysisArgs& a, cudaStream_t st) {
+  if (a.nblocks <= 0) return PFB_OK;
+  if (p->low_fast) {
+    bool done = false;
+    int rc = low_analysis_launch<T>(a, p->d_low_taps, st, &done);
+    if (rc) return fail(PFB_ERR_CUDA, "pfb_analysis_low launch: %s", cudaGetErrorString((cudaError_t)rc));
+    if (done) return check_launch("pfb_analysis_low");
+  }
+  const int ld = padded_len<T>(a.N);
+  int kb = 4096 / (a.N * a.npol);
+  if (kb < 1) kb = 1;
+  a.kb = kb;
+  const size_t smem = (size_t)kb * a.npol * ld * sizeof(Cx<T>);
+  int rc = set_smem(pfb_analysis_generic<T>, smem);
+  if (rc) return rc;
+  const long long grid = (a.nblocks + kb - 1) / kb;
+  if (grid > 2147483647ll) return fail(PFB_ERR_ARG, "too many blocks for one launch");
+  pfb_analysis_generic<T><<<(unsigned)grid, 256, smem, st>>>(a);
+  return check_launch("pfb_analysis_generic");
+}
+
+static int analysis_run(pfb_analysis_plan* p, const void* in, long long n_local, long long sample0, void* out,
+                        int npol, long long k_first, long long nblk, long long kout0, long long kout_mod,
+                        int first_call, void* stream) {
+  if (!p || !in || !out) return fail(PFB_ERR_ARG, "null pointer");
+  if (npol < 1 || npol > 2) return fail(PFB_ERR_ARG, "npol must be 1 or 2");
+  CU(cudaSetDevice(p->device));
+  AnalysisArgs a;
+  memset(&a, 0, sizeof(a));
+  a.in = in; a.out = out; a.taps = p->d_taps; a.fft = p->fft;
+  a.N = p->N; a.S = p->S; a.P = p->P; a.npol = npol;
+  a.n_dat = n_local;
+  long long start_abs0 = 0, rot = 0;
+  if (p->variant == PFB_VARIANT_PADDED) { start_abs0 = -(long long)p->fl; rot = 1; }
+  if (p->variant == PFB_VARIANT_LOWCBF) { start_abs0 = first_call ? -1536 : 0; rot = first_call ? 1536 : 0; }
+  a.start0 = start_abs0 + k_first * (long long)p->S - sample0;
+  a.phase0 = sample0 + rot;
+  a.nblocks = nblk; a.kout0 = kout0; a.kout_mod = kout_mod;
+  a.chan_first = p->chan_first; a.nchan_out = p->nchan_out; a.scale = p->scale;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  return p->dtype == PFB_DTYPE_C64 ? analysis_launch<float>(p, a, st) : analysis_launch<double>(p, a, st);
+}
+
+int pfb_analysis_execute(pfb_analysis_plan* plan, const void* in_dev, void* out_dev, int npol, long long n_dat,
+                         int first_call, void* stream) {
+  if (!plan) return fail(PFB_ERR_ARG, "null plan");
+  const long long nb = pfb_analysis_nblocks(plan, n_dat, first_call);
+  long long kout0 = 0, kmod = 0;
+  if (plan->variant == PFB_VARIANT_PADDED && nb > 0) {      // circshift(out,[0,0,-shift]) :156
+    kmod = nb;
+    kout0 = (nb - (plan->sds % nb)) % nb;
+  }
+  return analysis_run(plan, in_dev, n_dat, 0, out_dev, npol, 0, nb, kout0, kmod, first_call, stream);
+}
+
+int pfb_analysis_execute_segment(pfb_analysis_plan* plan, const void* in_dev, long long n_local, long long sample0,
+                                 void* out_dev, int npol, long long k_first, long long nblk, int first_call,
+                                 void* stream) {
+  if (!plan) return fail(PFB_ERR_ARG, "null plan");
+  if (plan->variant == PFB_VARIANT_PADDED)
+    return fail(PFB_ERR_UNSUPPORTED, "padded variant wraps its output circularly; segment form not defined");
+  if (k_first < 0 || nblk < 0) return fail(PFB_ERR_ARG, "negative block range");
+  return analysis_run(plan, in_dev, n_local, sample0, out_dev, npol, k_first, nblk, 0, 0, first_call, stream);
+}
+
+// ---------------------------------------------------------------------------
+static void freqz_half_host(const double* b, int nb, long long npoints, int neval, std::vector<double>* mag) {
+  mag->resize(neval);
+  for (int k = 0; k < neval; ++k) {
+    long double re = 0, im = 0;
+    for (int m = 0; m < nb; ++m) {
+      double c, s;
+      unit((long long)k * m, 2 * npoints, -1, &c, &s);   // exp(-i pi k m / npoints)
+      re += (long double)b[m] * c;
+      im += (long double)b[m] * s;
+    }
+    (*mag)[k] = (double)sqrtl(re * re + im * im);
+  }
+}
+
+template <typename T>
+static int inverse_build(pfb_inverse_plan* p, const double* taper, const double* dtaps, int ndtaps) {
+  int rc;
+  if ((rc = build_fft<T>(p->nchan, &p->fft_chan, &p->tabs))) return rc;
+  if ((rc = build_fft<T>(p->Nf, &p->fft_fwd, &p->tabs))) return rc;
+  if ((rc = build_fft<T>(p->FNw, &p->fft_bwd, &p->tabs))) return rc;
+  std::vector<T> tp(p->Nf);
+  for (int i = 0; i < p->Nf; ++i) tp[i] = taper ? (T)taper[i] : (T)1;
+  const T* dtp;
+  if ((rc = p->tabs.upload(tp, &dtp))) return rc;
+  p->d_taper = dtp;
+  // deripple weights in FN order (polyphase_synthesis.m:142-149, 244-250)
+  const int pb = p->FNw / 2;
+  std::vector<double> w(p->FNw, 1.0);
+  if (ndtaps > 0) {
+    std::vector<double> mag;
+    freqz_half_host(dtaps, ndtaps, (long long)p->nchan * pb, pb + 1, &mag);
+    for (int i = 0; i < pb; ++i) {
+      w[i] = 1.0 / mag[pb - i];
+      w[pb + i] = 1.0 / mag[i];
+    }
+  }
+  // W[t1][r] = D[r] (de/nu)/oN exp(+2 pi i (r-off) t1 / oN)
+  const long long oN = (long long)p->nchan * p->FNw;
+  const double g = ((double)p->de / p->nu) / (double)oN;
+  std::vector<Cx<T>> wt((size_t)p->nchan * p->FNw);
+  for (int t1 = 0; t1 < p->nchan; ++t1)
+    for (int r = 0; r < p->FNw; ++r) {
+      double c, s;
+      unit((long long)(r - p->off) * t1, oN, +1, &c, &s);
+      wt[(size_t)t1 * p->FNw + r].x = (T)(w[r] * g * c);
+      wt[(size_t)t1 * p->FNw + r].y = (T)(w[r] * g * s);
+    }
+  const Cx<T>* dwt;
+  if ((rc = p->tabs.upload(wt, &dwt))) return rc;
+  p->d_wt = dwt;
+  if (p->combine > 1) {                                       // polyphase_synthesis.m:198-238
+    std::vector<int> jm(p->nchan);
+    const int per = p->nchan / p->combine;
+    for (int chan = 0; chan < p->nchan; ++chan) {
+      int fine = (chan + per / 2) % p->nchan;
+      int coarse = fine / per;
+      fine -= coarse * per;
+      coarse = (coarse + p->combine / 2) % p->combine;
+      fine = (fine + per / 2) % per;
+      jm[chan] = coarse * per + fine;
+    }
+    const int* djm;
+    if ((rc = p->tabs.upload(jm, &djm))) return rc;
+    p->d_jmap = djm;
+  }
+  return low_inverse_plan_init<T>(p->nchan, p->nu, p->de, p->Nf, p->ov, p->spans, p->combine, tp, w, g,
+                                  &p->tabs.ptrs, &p->d_low, &p->low_fast);
+}
+
+int pfb_inverse_plan_create(pfb_inverse_plan** plan, int nchan, int os_nu, int os_de, int nfft, int overlap,
+                            const double* temporal_taper, const double* deripple_taps, int n_deripple_taps,
+                            int spans_nyquist, int combine, int dtype, int device) {
+  if (!plan || nchan < 1 || os_nu < 1 || os_de < 1 || os_de > os_nu || nfft < 2 || overlap < 0 || combine < 1)
+    return fail(PFB_ERR_ARG, "pfb_inverse_plan_create: bad argument");
+  if (dtype != PFB_DTYPE_C64 && dtype != PFB_DTYPE_C128) return fail(PFB_ERR_ARG, "dtype must be 0 (c64) or 1 (c128)");
+  if (((long long)nfft * os_de) % os_nu || ((long long)overlap * os_de) % os_nu)
+    return fail(PFB_ERR_ARG, "input_fft_length and input_overlap must be divisible by os_factor.nu");
+  if (nfft - 2 * overlap < 1) return fail(PFB_ERR_ARG, "input_overlap too large");
+  if (nchan % combine) return fail(PFB_ERR_ARG, "nchan must be a multiple of combine");
+  if (n_deripple_taps > 0 && !deripple_taps) return fail(PFB_ERR_ARG, "deripple taps missing");
+  CU(cudaSetDevice(device));
+  pfb_inverse_plan* p = new pfb_inverse_plan();
+  p->nchan = nchan; p->nu = os_nu; p->de = os_de; p->Nf = nfft; p->ov = overlap; p->dtype = dtype; p->device = device;
+  p->keep = nfft - 2 * overlap;
+  p->FNw = (int)(((long long)nfft * os_de) / os_nu);          // polyphase_synthesis.m:133
+  p->ov2 = (int)(((long long)overlap * os_de) / os_nu);
+  p->keep2 = p->FNw - 2 * p->ov2;
+  p->d2 = (nfft - p->FNw) / 2;                                 // :136
+  p->spans = spans_nyquist ? 1 : 0;
+  p->combine = combine;
+  p->off = p->spans ? p->FNw / 2 : 0;
+  if (p->FNw % 2 || (nfft - p->FNw) % 2) { delete p; return fail(PFB_ERR_ARG, "FN_width must be even"); }
+  int rc = dtype == PFB_DTYPE_C64 ? inverse_build<float>(p, temporal_taper, deripple_taps, n_deripple_taps)
+                                  : inverse_build<double>(p, temporal_taper, deripple_taps, n_deripple_taps);
+  if (rc) { delete p; return rc; }
+  *plan = p;
+  return PFB_OK;
+}
+
+int pfb_inverse_plan_destroy(pfb_inverse_plan* plan) {
+  if (plan) { cudaSetDevice(plan->device); delete plan; }
+  return PFB_OK;
+}
+
+long long pfb_inverse_nblocks(const pfb_inverse_plan* p, long long n_dat) {
+  if (!p) return PFB_ERR_ARG;
+  const long long nb = (n_dat - 2 * p->ov) / p->keep;          // polyphase_synthesis.m:114
+  return (n_dat < 2 * p->ov || nb < 0) ? 0 : nb;
+}
+
+long long pfb_inverse_out_len(const pfb_inverse_plan* p, long long n_dat) {
+  if (!p) return PFB_ERR_ARG;
+  return pfb_inverse_nblocks(p, n_dat) * (long long)p->keep2 * p->nchan;
+}
+
+int pfb_inverse_set_scratch_bytes(pfb_inverse_plan* p, long long bytes) {
+  if (!p || bytes < 0) return fail(PFB_ERR_ARG, "bad scratch size");
+  p->scratch_bytes = bytes;
+  return PFB_OK;
+}
+
+template <typename T>
+static int launch_chan_idft(pfb_inverse_plan* p, const void* in, void* out, int npol, long long nrows, cudaStream_t st) {
+  if (nrows <= 0) return PFB_OK;
+  if (p->low_fast) {
+    bool done = false;
+    int rc = low_chan_idft_launch<T>(p->d_low, in, out, npol, nrows, st, &done);
+    if (rc) return fail(PFB_ERR_CUDA, "pfb_chan_idft_low launch: %s", cudaGetErrorString((cudaError_t)rc));
+    if (done) return check_launch("pfb_chan_idft_low");
+  }
+  ChanIdftArgs a;
+  memset(&a, 0, sizeof(a));
+  a.in = in; a.out = out; a.fft = p->fft_chan; a.jmap = p->d_jmap; a.nchan = p->nchan; a.npol = npol; a.nrows = nrows;
+  int rb = 4096 / (p->nchan * npol);
+  if (rb < 1) rb = 1;
+  a.rb = rb;
+  const size_t smem = (size_t)rb * npol * padded_len<T>(p->nchan) * sizeof(Cx<T>);
+  int rc = set_smem(pfb_chan_idft_generic<T>, smem);
+  if (rc) return rc;
+  const long long grid = (nrows + rb - 1) / rb;
+  if (grid > 2147483647ll) return fail(PFB_ERR_ARG, "too many rows for one launch");
+  pfb_chan_idft_generic<T><<<(unsigned)grid, 256, smem, st>>>(a);
+  return check_launch("pfb_chan_idft_generic");
+}
+
+template <typename T>
+static int launch_resample(pfb_inverse_plan* p, const void* v, void* out, int npol, long long nblk, cudaStream_t st) {
+  if (nblk <= 0) return PFB_OK;
+  if (p->low_fast) {
+    bool done = false;
+    int rc = low_resample_launch<T>(p->d_low, v, out, npol, nblk, st, &done);
+    if (rc) return fail(PFB_ERR_CUDA, "pfb_resample_low launch: %s", cudaGetErrorString((cudaError_t)rc));
+    if (done) return check_launch("pfb_resample_low");
+  }
+  ResampleArgs a;
+  memset(&a, 0, sizeof(a));
+  a.v = v; a.out = out; a.fwd = p->fft_fwd; a.bwd = p->fft_bwd; a.taper = p->d_taper; a.wt = p->d_wt;
+  a.nchan = p->nchan; a.npol = npol; a.Nf = p->Nf; a.FNw = p->FNw; a.keep = p->keep; a.ov2 = p->ov2;
+  a.keep2 = p->keep2; a.off = p->off; a.d2 = p->d2;
+  const size_t percol = (size_t)(padded_len<T>(p->Nf) + padded_len<T>(p->FNw)) * sizeof(Cx<T>);
+  int tg = 1;
+  while (p->nchan % (tg * 2) == 0 && (size_t)(tg * 2) * npol * percol <= 110 * 1024) tg *= 2;
+  a.tg = tg;
+  const size_t smem = (size_t)tg * npol * percol;
+  int rc = set_smem(pfb_resample_generic<T>, smem);
+  if (rc) return rc;
+  const long long groups = p->nchan / tg;
+  // keep each launch's grid within 2^31 and the block count in an int
+  long long done = 0;
+  while (done < nblk) {
+    long long nb = nblk - done;
+    const long long maxb = 2000000000ll / groups;
+    if (nb > maxb) nb = maxb;
+    a.nblk = (int)nb;
+    const long long rowlen = (long long)p->nchan * npol;
+    a.v = reinterpret_cast<const Cx<T>*>(v) + done * p->keep * rowlen;
+    a.out = reinterpret_cast<Cx<T>*>(out) + done * p->keep2 * rowlen;
+    pfb_resample_generic<T><<<(unsigned)(nb * groups), 256, smem, st>>>(a);
+    rc = check_launch("pfb_resample_generic");
+    if (rc) return rc;
+    done += nb;
+  }
+  return PFB_OK;
+}
+
+template <typename T>
+static int inverse_run(pfb_inverse_plan* p, const void* in, void* out, int npol, long long n_dat, cudaStream_t st) {
+  const long long nblocks = pfb_inverse_nblocks(p, n_dat);
+  if (nblocks <= 0) return PFB_OK;
+  const long long rowbytes = (long long)p->nchan * npol * sizeof(Cx<T>);
+  long long B = (p->scratch_bytes - (long long)2 * p->ov * rowbytes) / ((long long)p->keep * rowbytes);
+  if (B < 1) B = 1;
+  if (B > nblocks) B = nblocks;
+  const size_t need = (size_t)(((B - 1) * p->keep + p->Nf) * rowbytes);
+  if (need > p->scratch_cap) {
+    if (p->d_scratch) CU(cudaFree(p->d_scratch));
+    p->d_scratch = nullptr; p->scratch_cap = 0;
+    CU(cudaMalloc(&p->d_scratch, need));
+    p->scratch_cap = need;
+  }
+  const long long rowlen = (long long)p->nchan * npol;
+  for (long long n0 = 0; n0 < nblocks; n0 += B) {
+    const long long nb = (nblocks - n0 < B) ? nblocks - n0 : B;
+    const long long rows = (nb - 1) * p->keep + p->Nf;
+    const Cx<T>* src = reinterpret_cast<const Cx<T>*>(in) + n0 * p->keep * rowlen;
+    int rc = launch_chan_idft<T>(p, src, p->d_scratch, npol, rows, st);
+    if (rc) return rc;
+    Cx<T>* dst = reinterpret_cast<Cx<T>*>(out) + n0 * p->keep2 * rowlen;
+    rc = launch_resample<T>(p, p->d_scratch, dst, npol, nb, st);
+    if (rc) return rc;
+  }
+  return PFB_OK;
+}
+
+int pfb_inverse_execute(pfb_inverse_plan* p, const void* in_dev, void* out_dev, int npol, long long n_dat,
+                        void* stream) {
+  if (!p || !in_dev || !out_dev) return fail(PFB_ERR_ARG, "null pointer");
+  if (npol < 1 || npol > 2) return fail(PFB_ERR_ARG, "npol must be 1 or 2");
+  CU(cudaSetDevice(p->device));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  return p->dtype == PFB_DTYPE_C64 ? inverse_run<float>(p, in_dev, out_dev, npol, n_dat, st)
+                                   : inverse_run<double>(p, in_dev, out_dev, npol, n_dat, st);
+}
+
+int pfb_inverse_execute_stage(pfb_inverse_plan* p, int stage, const void* in_dev, void* out_dev, int npol,
+                              long long n_dat, void* stream) {
+  if (!p || !in_dev || !out_dev) return fail(PFB_ERR_ARG, "null pointer");
+  if (npol < 1 || npol > 2) return fail(PFB_ERR_ARG, "npol must be 1 or 2");
+  CU(cudaSetDevice(p->device));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const bool f32 = p->dtype == PFB_DTYPE_C64;
+  if (stage == 0) return f32 ? launch_chan_idft<float>(p, in_dev, out_dev, npol, n_dat, st)
+                             : launch_chan_idft<double>(p, in_dev, out_dev, npol, n_dat, st);
+  if (stage == 1) {
+    const long long nb = pfb_inverse_nblocks(p, n_dat);
+    return f32 ? launch_resample<float>(p, in_dev, out_dev, npol, nb, st)
+               : launch_resample<double>(p, in_dev, out_dev, npol, nb, st);
+  }
+  return fail(PFB_ERR_ARG, "stage must be 0 or 1");
+}
+

@@ -1,0 +1,193 @@
+// Generic (any N / taps / OS ratio / precision) kernels for the PFB hot path.
+// These are the always-correct path; the Low-specific fast kernels live in
+// pfb_low.cuh and are selected by the plan when the shape matches.
+#pragma once
+#include "fft_smem.cuh"
+
+namespace pfb {
+
+// ---------------------------------------------------------------------------
+// K1g: polyphase FIR commutator + N-point forward FFT + phase rotation.
+// Covers polyphase_analysis.m:83-122, polyphase_analysis_padded.m:106-156 and
+// PSTFilterbank.m:25-45 through one closed form:
+//   out[c,k] = scale * sum_n f[n] x[t0_k+n] W^{c (phase0+t0_k+n)},  t0_k = start0 + k S
+// The W^{c*shift} rotation is free: the arm sum for tap index n is written to
+// FFT input slot (phase0+t0_k+n) mod N.
+// ---------------------------------------------------------------------------
+struct AnalysisArgs {
+  const void* in;        // [t][pol] complex
+  void* out;             // [k][chan][pol] complex
+  const void* taps;      // T[P*N] (zero padded; reversed for the padded variant)
+  FftDev fft;            // forward N
+  int N, S, P, npol;
+  long long n_dat;       // valid samples in `in`
+  long long start0;      // window start of block 0 (relative to in[0], may be < 0)
+  long long phase0;      // absolute index of in[0] + extra rotation
+  long long nblocks;     // blocks computed by this launch
+  long long kout0;       // output block slot = (k + kout0) mod kout_mod
+  long long kout_mod;
+  int chan_first;        // FFT bin of output channel 0
+  int nchan_out;
+  double scale;
+  int kb;                // blocks per CTA
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) pfb_analysis_generic(const AnalysisArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Cx<T>* s = reinterpret_cast<Cx<T>*>(smem_raw);
+  const int N = a.N, npol = a.npol, ld = padded_len<T>(N);
+  const long long k0 = (long long)blockIdx.x * a.kb;
+  const int kb = (int)min((long long)a.kb, a.nblocks - k0);
+  const Cx<T>* __restrict__ x = reinterpret_cast<const Cx<T>*>(a.in);
+  const T* __restrict__ f = reinterpret_cast<const T*>(a.taps);
+
+  // FIR: work item = (kk, j, pol), pol fastest -> coalesced over [t][pol]
+  const int items = kb * N * npol;
+  for (int e = threadIdx.x; e < items; e += blockDim.x) {
+    const int pol = e % npol;
+    const int j = (e / npol) % N;
+    const int kk = e / (npol * N);
+    const long long t0 = a.start0 + (k0 + kk) * (long long)a.S;
+    T accx = 0, accy = 0;
+    for (int m = 0; m < a.P; ++m) {
+      const long long t = t0 + j + (long long)m * N;
+      if (t >= 0 && t < a.n_dat) {
+        const Cx<T> v = ldg_cx<T>(x + t * npol + pol);
+        const T c = __ldg(f + j + m * N);
+        accx += c * v.x;
+        accy += c * v.y;
+      }
+    }
+    const int slot = pmod(a.phase0 + t0 + j, N);
+    s[(size_t)(kk * npol + pol) * ld + padi<T>(slot)] = mk<T>(accx, accy);
+  }
+  __syncthreads();
+  fft_smem<T, -1, false>(s, ld, kb * npol, a.fft);
+
+  Cx<T>* __restrict__ out = reinterpret_cast<Cx<T>*>(a.out);
+  const T scale = (T)a.scale;
+  const int nco = a.nchan_out;
+  const int oitems = kb * nco * npol;
+  for (int e = threadIdx.x; e < oitems; e += blockDim.x) {
+    const int pol = e % npol;
+    const int ci = (e / npol) % nco;
+    const int kk = e / (npol * nco);
+    int c = ci + a.chan_first;
+    if (c >= N) c -= N;
+    const Cx<T> v = s[(size_t)(kk * npol + pol) * ld + padi<T>(__ldg(a.fft.perm + c))];
+    long long ko = k0 + kk + a.kout0;
+    if (a.kout_mod > 0) ko %= a.kout_mod;
+    out[(ko * nco + ci) * npol + pol] = v * scale;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// K2g: the nchan-point inverse DFT across channels, hoisted in front of the
+// per-channel FFTs (polyphase_synthesis.m:285 factored as nchan x FN_width,
+// SURVEY §7 design note).  One row per fine-channel time sample.
+//   v[tau][t1][pol] = sum_ch u[tau][jmap[ch]][pol] exp(+2 pi i ch t1 / nchan)
+// ---------------------------------------------------------------------------
+struct ChanIdftArgs {
+  const void* in;       // [tau][chan][pol]
+  void* out;            // [tau][t1][pol]
+  FftDev fft;           // nchan (used as inverse, DIT)
+  const int* jmap;      // combine re-order (polyphase_synthesis.m:198-238) or null
+  int nchan, npol;
+  long long nrows;
+  int rb;               // rows per CTA
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) pfb_chan_idft_generic(const ChanIdftArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Cx<T>* s = reinterpret_cast<Cx<T>*>(smem_raw);
+  const int n = a.nchan, npol = a.npol, ld = padded_len<T>(n);
+  const long long r0 = (long long)blockIdx.x * a.rb;
+  const int rb = (int)min((long long)a.rb, a.nrows - r0);
+  const Cx<T>* __restrict__ u = reinterpret_cast<const Cx<T>*>(a.in);
+  const int items = rb * n * npol;
+  for (int e = threadIdx.x; e < items; e += blockDim.x) {
+    const int pol = e % npol;
+    const int ch = (e / npol) % n;
+    const int r = e / (npol * n);
+    const int src = a.jmap ? __ldg(a.jmap + ch) : ch;
+    const Cx<T> v = ldg_cx<T>(u + ((r0 + r) * n + src) * npol + pol);
+    s[(size_t)(r * npol + pol) * ld + padi<T>(__ldg(a.fft.perm + ch))] = v;
+  }
+  __syncthreads();
+  fft_smem<T, +1, true>(s, ld, rb * npol, a.fft);
+  Cx<T>* __restrict__ out = reinterpret_cast<Cx<T>*>(a.out);
+  for (int e = threadIdx.x; e < items; e += blockDim.x) {
+    const int pol = e % npol;
+    const int t1 = (e / npol) % n;
+    const int r = e / (npol * n);
+    out[((r0 + r) * n + t1) * npol + pol] = s[(size_t)(r * npol + pol) * ld + padi<T>(t1)];
+  }
+}
+
+// ---------------------------------------------------------------------------
+// K3g: per output phase t1 (column of v) overlap-save resampling:
+// taper -> Nf-point FFT -> keep FN_width bins (fftshift + discard) -> deripple x
+// stitch twiddle x 1/(OS*oN) -> FN_width-point inverse FFT -> drop the output
+// overlap.  polyphase_synthesis.m:163-302 for one column.
+//   out[(n*keep2 + t2 - ov2)*nchan + t1] = sum_r Z[r] exp(2 pi i (r-off) t2/FNw),
+//   Z[r] = W[t1][r] * FFT_Nf(taper * v[n*keep : n*keep+Nf, t1])[(r+d2+Nf/2) mod Nf]
+// ---------------------------------------------------------------------------
+struct ResampleArgs {
+  const void* v;        // [tau][t1][pol]  (local chunk, row 0 = first tau of block 0)
+  void* out;            // [T2][t1][pol]   (local chunk)
+  FftDev fwd;           // Nf forward (DIF)
+  FftDev bwd;           // FNw inverse (DIT)
+  const void* taper;    // T[Nf]
+  const void* wt;       // Cx<T>[nchan][FNw]
+  int nchan, npol, Nf, FNw, keep, ov2, keep2, off, d2;
+  int tg;               // t1 values per CTA
+  int nblk;             // overlap-save blocks in this launch
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) pfb_resample_generic(const ResampleArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int ncol = a.tg * a.npol;
+  const int ldA = padded_len<T>(a.Nf), ldB = padded_len<T>(a.FNw);
+  Cx<T>* sA = reinterpret_cast<Cx<T>*>(smem_raw);
+  Cx<T>* sB = sA + (size_t)ncol * ldA;
+  const int groups = a.nchan / a.tg;
+  const int g = blockIdx.x % groups;
+  const long long nb = blockIdx.x / groups;
+  const int t1_0 = g * a.tg;
+  const long long rowlen = (long long)a.nchan * a.npol;
+  const Cx<T>* __restrict__ v = reinterpret_cast<const Cx<T>*>(a.v) + nb * a.keep * rowlen + (long long)t1_0 * a.npol;
+  const T* __restrict__ taper = reinterpret_cast<const T*>(a.taper);
+
+  for (int e = threadIdx.x; e < a.Nf * ncol; e += blockDim.x) {
+    const int col = e % ncol, tau = e / ncol;
+    const Cx<T> val = ldg_cx<T>(v + tau * rowlen + col);
+    sA[(size_t)col * ldA + padi<T>(tau)] = val * __ldg(taper + tau);
+  }
+  __syncthreads();
+  fft_smem<T, -1, false>(sA, ldA, ncol, a.fwd);
+
+  const Cx<T>* __restrict__ wt = reinterpret_cast<const Cx<T>*>(a.wt);
+  for (int e = threadIdx.x; e < a.FNw * ncol; e += blockDim.x) {
+    const int r = e % a.FNw, col = e / a.FNw;
+    const int t1 = t1_0 + col / a.npol;
+    int b = r + a.d2 + a.Nf / 2;
+    if (b >= a.Nf) b -= a.Nf;
+    int rp = r - a.off;
+    if (rp < 0) rp += a.FNw;
+    const Cx<T> z = sA[(size_t)col * ldA + padi<T>(__ldg(a.fwd.perm + b))] * ldg_cx<T>(wt + (size_t)t1 * a.FNw + r);
+    sB[(size_t)col * ldB + padi<T>(__ldg(a.bwd.perm + rp))] = z;
+  }
+  __syncthreads();
+  fft_smem<T, +1, true>(sB, ldB, ncol, a.bwd);
+
+  Cx<T>* __restrict__ out = reinterpret_cast<Cx<T>*>(a.out) + nb * a.keep2 * rowlen + (long long)t1_0 * a.npol;
+  for (int e = threadIdx.x; e < a.keep2 * ncol; e += blockDim.x) {
+    const int col = e % ncol, i = e / ncol;
+    out[i * rowlen + col] = sB[(size_t)col * ldB + padi<T>(i + a.ov2)];
+  }
+}
+
+}  // namespace pfb

@@ -1,0 +1,211 @@
+"""GPU parity: the CUDA path through the C ABI vs the numpy oracle on the same
+seeded inputs.  Tolerances (north star): normalised max error <= 1e-5 in fp32,
+<= 1e-6 in fp64 mode (we assert 1e-10 there)."""
+import numpy as np
+import pytest
+
+from oracle import pfb_oracle as o
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"c64": 1e-5, "c128": 1e-10}
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def nerr(a, b):
+    return float(np.abs(a - b).max() / np.abs(b).max())
+
+
+def cnoise(rng, shape):
+    return rng.standard_normal(shape) + 1j * rng.standard_normal(shape)
+
+
+def to_dev(x_pct, dt):
+    """oracle layout (npol, 1|nchan, ndat) -> device TFP tensor."""
+    torch = _torch()
+    a = np.ascontiguousarray(np.transpose(x_pct, (2, 1, 0)))
+    if a.shape[1] == 1 and x_pct.shape[1] == 1:
+        a = a[:, 0, :]
+    t = torch.from_numpy(a.astype(np.complex64 if dt == "c64" else np.complex128))
+    return t.cuda()
+
+
+def from_dev(t):
+    a = t.cpu().numpy()
+    if a.ndim == 2:
+        a = a[:, None, :]
+    return np.transpose(a, (2, 1, 0))
+
+
+def _lowpass(nchan):
+    from scipy.signal import firwin
+    return firwin(nchan * 6 + 1, 1.0 / nchan)
+
+
+def tdtype(dt):
+    torch = _torch()
+    return torch.complex64 if dt == "c64" else torch.complex128
+
+
+ANALYSIS_CASES = [
+    # nchan, os, ntaps, extra samples, npol
+    (256, "4/3", 3072, 192 * 50 + 17, 2),
+    (256, "4/3", 3072, 192 * 9, 1),
+    (8, "8/7", 3072, 7 * 300 + 3, 1),
+    (8, "8/7", 81, 1000, 2),
+    (16, "4/3", 97, 1500, 2),
+    (256, "32/27", 6144, 216 * 20, 2),
+    (64, "1/1", 64 * 4, 64 * 30, 1),
+    (512, "8/7", 512 * 5 + 1, 448 * 12, 2),
+    (4096, "8/7", 4096 * 3 - 5, 3584 * 4 + 100, 2),
+]
+
+
+@pytest.mark.parametrize("dt", ["c64", "c128"])
+@pytest.mark.parametrize("nchan,osf,ntaps,extra,npol", ANALYSIS_CASES)
+def test_analysis_bunton(nchan, osf, ntaps, extra, npol, dt, pst_taps):
+    from ska_pst_dsp_model_b200 import ops
+    rng = np.random.default_rng(nchan + ntaps)
+    h = pst_taps / pst_taps.sum() if ntaps == 3072 else rng.standard_normal(ntaps) / np.sqrt(ntaps)
+    fl = -(-ntaps // nchan) * nchan
+    x = cnoise(rng, (npol, 1, fl + extra))
+    ref = o.polyphase_analysis(x, h, nchan, osf)
+    plan = ops.AnalysisPlan(nchan, osf, h, "polyphase_analysis", dtype=tdtype(dt))
+    got = from_dev(plan(to_dev(x, dt)))
+    assert got.shape == ref.shape
+    assert nerr(got, ref) < TOL[dt]
+
+
+@pytest.mark.parametrize("dt", ["c64", "c128"])
+@pytest.mark.parametrize("nchan,osf,ntaps,ndat,npol", [
+    (16, "8/7", 16 * 25 + 1, 3000, 2),
+    (8, "4/3", 50, 999, 1),
+    (512, "8/7", 512 * 24 + 1, 448 * 40 + 11, 2),
+    (4096, "8/7", 4096 * 2 + 1, 3584 * 6, 1),
+])
+def test_analysis_padded(nchan, osf, ntaps, ndat, npol, dt):
+    from ska_pst_dsp_model_b200 import ops
+    rng = np.random.default_rng(ntaps)
+    h = rng.standard_normal(ntaps) / np.sqrt(ntaps)
+    x = cnoise(rng, (npol, 1, ndat))
+    ref = o.polyphase_analysis_padded(x, h, nchan, osf)
+    plan = ops.AnalysisPlan(nchan, osf, h, "polyphase_analysis_padded", dtype=tdtype(dt))
+    got = from_dev(plan(to_dev(x, dt)))
+    assert got.shape == ref.shape
+    assert nerr(got, ref) < TOL[dt]
+
+
+@pytest.mark.parametrize("dt", ["c64", "c128"])
+@pytest.mark.parametrize("first", [True, False])
+def test_analysis_lowcbf(dt, first, pst_taps):
+    from ska_pst_dsp_model_b200 import ops
+    rng = np.random.default_rng(9)
+    x = cnoise(rng, (2, 1, 3072 + 192 * 31 + 5))
+    ref = o.polyphase_analysis_lowcbf(x, pst_taps, do_padding=first)
+    plan = ops.AnalysisPlan(256, "4/3", pst_taps, "polyphase_analysis_lowcbf", dtype=tdtype(dt))
+    got = from_dev(plan(to_dev(x, dt), first_call=first))
+    assert got.shape == ref.shape and got.shape[1] == 216
+    assert nerr(got, ref) < TOL[dt]
+
+
+INVERSE_CASES = [
+    # nchan, os, nfft, ov, spans, combine, deripple, taper, nblocks-ish, npol
+    (256, "4/3", 256, 48, True, 1, True, "tukey", 7, 2),
+    (256, "4/3", 256, 48, True, 1, False, "no_window", 3, 1),
+    (8, "8/7", 256, 48, True, 1, True, "tukey", 20, 1),
+    (8, "8/7", 64, 8, False, 1, False, "top_hat", 9, 2),
+    (16, "4/3", 48, 12, False, 4, False, "tukey", 11, 2),
+    (192, "4/3", 256, 48, False, 1, False, "tukey", 3, 1),
+    (3072, "4/3", 128, 16, False, 16, False, "tukey", 2, 1),
+    (256, "32/27", 256, 32, True, 1, True, "tukey", 3, 2),
+    (512, "8/7", 512, 128, True, 1, True, "tukey", 3, 2),
+    (4096, "8/7", 512, 128, True, 1, False, "tukey", 2, 1),
+    (256, "4/3", 1024, 128, True, 1, True, "tukey", 2, 2),
+]
+
+
+@pytest.mark.parametrize("dt", ["c64", "c128"])
+@pytest.mark.parametrize("nchan,osf,nfft,ov,spans,comb,dr,tap,nb,npol", INVERSE_CASES)
+def test_inversion(nchan, osf, nfft, ov, spans, comb, dr, tap, nb, npol, dt, pst_taps):
+    from ska_pst_dsp_model_b200 import ops
+    rng = np.random.default_rng(nchan * 7 + nfft)
+    ndat = (nfft - 2 * ov) * nb + 2 * ov + 5
+    x = cnoise(rng, (npol, nchan, ndat))
+    if dr:
+        h = pst_taps / pst_taps.sum() if nchan == 256 and osf == "4/3" else _lowpass(nchan)
+    else:
+        h = None
+    taper = o.make_temporal_taper(tap, nfft, ov)
+    ref = o.polyphase_synthesis(x, spans, nfft, osf, h, 1, ov, taper, None, comb)
+    plan = ops.InversePlan(nchan, osf, nfft, ov, tap, deripple_taps=h, spans_nyquist=spans, combine=comb,
+                           dtype=tdtype(dt))
+    got = from_dev(plan(to_dev(x, dt)))
+    assert got.shape == ref.shape and got.shape[2] > 0
+    assert nerr(got, ref) < TOL[dt]
+
+
+@pytest.mark.parametrize("dt", ["c64", "c128"])
+def test_inversion_chunked_scratch_and_offset(dt, pst_taps):
+    """Small L2 scratch forces many chunks; sample_offset > 1."""
+    from ska_pst_dsp_model_b200 import ops
+    rng = np.random.default_rng(3)
+    x = cnoise(rng, (2, 256, 160 * 9 + 96 + 4))
+    h = pst_taps / pst_taps.sum()
+    ref = o.polyphase_synthesis(x, True, 256, "4/3", h, 3, 48, o.window_tukey(256, 48))
+    plan = ops.InversePlan(256, "4/3", 256, 48, "tukey", deripple_taps=h, dtype=tdtype(dt))
+    plan.set_scratch_bytes(3 * 160 * 256 * 2 * 16)
+    got = from_dev(plan(to_dev(x, dt), sample_offset=3))
+    assert got.shape == ref.shape
+    assert nerr(got, ref) < TOL[dt]
+
+
+def test_round_trip_impulse_criteria(pst_taps):
+    """TestImpulse.m:46-73 on the GPU chain: peak where sgcht.m:466-473 puts it,
+    everything else below -60 dB."""
+    torch = _torch()
+    from ska_pst_dsp_model_b200 import ops
+    h = pst_taps / pst_taps.sum()
+    n = 256 * 192 * 3
+    off = 30000
+    x = torch.zeros((n, 2), dtype=torch.complex64, device="cuda")
+    x[off, :] = 1.0
+    ch = ops.AnalysisPlan(256, "4/3", h)(x)
+    y = ops.InversePlan(256, "4/3", 256, 48, "tukey", deripple_taps=h)(ch).cpu().numpy()
+    expect = off - 3072 // 2 - (36 * 256 - 1 + 1)
+    for p in range(2):
+        a = np.abs(y[:, p])
+        assert int(a.argmax()) == expect
+        a[expect - 1: expect + 2] = 0
+        assert 20 * np.log10(a.max()) < -60
+
+
+def test_segment_equals_oneshot(pst_taps):
+    from ska_pst_dsp_model_b200 import ops
+    torch = _torch()
+    rng = np.random.default_rng(11)
+    h = pst_taps / pst_taps.sum()
+    x = torch.from_numpy(cnoise(rng, (3072 + 192 * 64, 2)).astype(np.complex64)).cuda()
+    plan = ops.AnalysisPlan(256, "4/3", h)
+    full = plan(x)
+    # second half as a segment with its FIR halo, from a buffer that starts mid-stream
+    k_first, nblk = 29, 35
+    s0 = k_first * 192 - 7
+    seg = plan.segment(x[s0: s0 + 7 + nblk * 192 + 2880].contiguous(), s0, k_first, nblk)
+    assert torch.equal(seg, full[k_first:k_first + nblk])
+
+
+def test_errors_are_loud():
+    from ska_pst_dsp_model_b200 import ops
+    from ska_pst_dsp_model_b200.lib import PfbError
+    torch = _torch()
+    with pytest.raises(PfbError):
+        ops.AnalysisPlan(10 * 11, "1/1", np.ones(110 * 2))          # 11 is not a supported radix
+    with pytest.raises(PfbError):
+        ops.InversePlan(8, "8/7", 60, 8)                            # Nf not divisible by nu
+    plan = ops.AnalysisPlan(8, "8/7", np.ones(81))
+    with pytest.raises(TypeError):
+        plan(torch.zeros((100, 1), dtype=torch.complex64))          # CPU tensor: no fallback
