@@ -1,0 +1,442 @@
+#!/usr/bin/env python
+"""Benchmark of the PFB analysis + inversion hot path (BASELINE.json metric:
+input Msamples/s, analysis+inversion, with HBM GB/s vs roofline).
+
+  python bench.py --gpus 1 --steps 10 --warmup 3            # B200 arm
+  python bench.py --impl reference --steps 3 --warmup 1     # CPU reference arm
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+      --master-port P bench.py --gpus N ...                  # N > 1 (one rank per GPU)
+
+Workload (configs[1]): SKA-Low PST round trip - 256 channels, OS 4/3,
+3072-tap PST filter, polyphase_analysis + polyphase_synthesis inversion (Nf=256,
+overlap 48, tukey taper, deripple), dual-pol, 2^24 complex64 samples per pol and
+per GPU.  A "step" is one full pass: (halo exchange when N>1) + analysis kernel +
+inversion kernel chain over the rank's time shard.  At N>1 the stream is N times
+longer and time-sharded (weak scaling); the only collective is the neighbour halo
+send/recv (ska_pst_dsp_model_b200/sharding.py).
+
+One JSON line is printed by rank 0.  `value` = device-resident throughput,
+`e2e` = the same through the public API with pinned HOST buffers (H2D + D2H inside
+the timed region).  `roofline` describes the dominant kernel.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+NCHAN, OS, NFFT, OVERLAP, NPOL = 256, "4/3", 256, 48, 2
+METRIC = "input Msamples/s (PFB analysis + inversion round trip)"
+UNIT = "Msamples/s"
+
+
+def workload_config(log2n, world):
+    return {
+        "workload": f"SKA-Low PST round trip: {NCHAN} ch, OS {OS}, 3072-tap PST filter, Nf={NFFT}, overlap={OVERLAP}, "
+                    f"tukey+deripple, {NPOL} pol x 2^{log2n} complex64 samples per GPU",
+        "channels": NCHAN, "os_factor": OS, "fir_taps": 3072, "input_fft_length": NFFT, "input_overlap": OVERLAP,
+        "n_pol": NPOL, "samples_per_pol_per_gpu": 1 << log2n, "global_samples_per_pol": world << log2n,
+        "parallelism": f"time-shard x{world}" if world > 1 else "single GPU",
+        "l2": "inputs (256 MiB/GPU) and outputs larger than the 126 MB L2; no flush needed",
+    }
+
+
+# --------------------------------------------------------------------------
+# synthetic stream: 32-tone comb (sgcht.m:394-432) + an impulse every output_keep
+# samples, a pure function of the absolute sample index (any shard can be
+# regenerated; no RNG)
+# --------------------------------------------------------------------------
+def comb_params():
+    import numpy as np
+    amps = np.linspace(1.0, 2.0 ** 0.5, 32)
+    fmin = -0.5 + 1.0 / 128 + 1.0 / (NCHAN * 4)
+    freqs = np.linspace(fmin, fmin + 31.0 / 32, 32)
+    return amps, freqs
+
+
+def synth_numpy(t0, n, npol):
+    import numpy as np
+    amps, freqs = comb_params()
+    t = np.arange(t0, t0 + n, dtype=np.float64)
+    x = np.zeros(n, dtype=np.complex128)
+    for a, f in zip(amps, freqs):
+        x += a * np.exp(2j * np.pi * np.mod(f * t, 1.0))
+    x /= 32.0
+    x[(np.arange(t0, t0 + n) % 30720) == 0] += 1.0
+    return np.repeat(x.astype(np.complex64)[:, None], npol, axis=1)
+
+
+def synth_torch(t0, n, npol, device):
+    import torch
+    amps, freqs = comb_params()
+    out = torch.empty((n, npol), dtype=torch.complex64, device=device)
+    chunk = 1 << 21
+    for c0 in range(0, n, chunk):
+        m = min(chunk, n - c0)
+        t = torch.arange(t0 + c0, t0 + c0 + m, dtype=torch.float64, device=device)
+        acc = torch.zeros(m, dtype=torch.complex128, device=device)
+        for a, f in zip(amps, freqs):
+            ph = torch.remainder(t * float(f), 1.0) * (2 * torch.pi)
+            acc += float(a) * torch.polar(torch.ones_like(ph), ph)
+        acc /= 32.0
+        ti = torch.arange(t0 + c0, t0 + c0 + m, dtype=torch.int64, device=device)
+        acc[(ti % 30720) == 0] += 1.0
+        out[c0:c0 + m] = acc.to(torch.complex64)[:, None]
+    return out
+
+
+# --------------------------------------------------------------------------
+# CPU reference arm: the numpy oracle (port of the Matlab model) on all host cores
+# --------------------------------------------------------------------------
+_CPU = {}
+
+
+def _cpu_worker(job):
+    import numpy as np
+    from oracle import pfb_oracle as orc
+    seg_in0, seg_n, out0, out_n = job
+    x = _CPU["x"][seg_in0: seg_in0 + seg_n]                      # [t][pol]
+    xo = np.ascontiguousarray(x.T[:, None, :])
+    ch = orc.polyphase_analysis(xo, _CPU["taps"], NCHAN, OS)
+    y = orc.polyphase_synthesis(ch, True, NFFT, OS, _CPU["taps"], 1, OVERLAP, _CPU["taper"])
+    out = np.frombuffer(_CPU["out"], dtype=np.complex64).reshape(-1, NPOL)
+    out[out0: out0 + out_n] = y[:, 0, :out_n].T
+    return out_n
+
+
+def cpu_round_trip_setup(log2n, workers):
+    import multiprocessing as mp
+    import numpy as np
+    from oracle import pfb_oracle as orc
+    from ska_pst_dsp_model_b200.filters import load_pst_taps
+    from ska_pst_dsp_model_b200.sharding import plan_time_shards
+    n = 1 << log2n
+    shards = plan_time_shards(n, workers * 4, NCHAN, OS, 3072, NFFT, OVERLAP)
+    _CPU["x"] = synth_numpy(0, n, NPOL)
+    _CPU["taps"] = load_pst_taps(normalise=True)
+    _CPU["taper"] = orc.window_tukey(NFFT, OVERLAP)
+    total_out = shards[-1].out0 + shards[-1].out_n
+    _CPU["out"] = mp.RawArray("f", total_out * NPOL * 2)
+    # the reference's nblocks = floor((n_dat - fl)/step) (polyphase_analysis.m:62) is one
+    # short of what fits, so hand each segment one extra step of input
+    jobs = [(s.need0, s.need_n + 192, s.out0, s.out_n) for s in shards]
+    pool = mp.get_context("fork").Pool(workers)
+    return pool, jobs, n * NPOL
+
+
+def run_reference(args):
+    """`--impl reference`: the oracle port on the host cores, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    workers = min(os.cpu_count() or 1, 64)
+    log2n = args.cpu_log2_samples
+    pool, jobs, samples = cpu_round_trip_setup(log2n, workers)
+    for _ in range(args.warmup):
+        pool.map(_cpu_worker, jobs)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        pool.map(_cpu_worker, jobs)
+    dt = (time.perf_counter() - t0) / args.steps
+    pool.close()
+    value = samples / dt / 1e6
+    sample = f"first 2^{log2n} samples/pol x {NPOL} pol of the same synthetic stream per step, {len(jobs)} time segments"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args.log2_samples, args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "numpy port of the reference's Matlab model (oracle/pfb_oracle.py); the reference itself cannot "
+                "run here (Matlab / un-vendored pfb package)",
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# --------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t_begin, t_end):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons, power = [], None, set(), []
+        for ts, line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                clk, mx = float(parts[1]), float(parts[2])
+            except ValueError:
+                continue
+            smax = mx
+            if t_begin - 0.05 <= ts <= t_end + 0.05:
+                sm.append(clk)
+                try:
+                    power.append(float(parts[3]))
+                except ValueError:
+                    pass
+                names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+                for nm, val in zip(names, parts[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": smax,
+                "reasons": sorted(reasons), "samples": len(sm), "power_w_max": max(power) if power else None}
+
+
+def load_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            with open(p) as f:
+                return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def load_traffic():
+    p = os.path.join(ROOT, "profiles", "dram_traffic.json")
+    if os.path.exists(p):
+        try:
+            with open(p) as f:
+                return json.load(f)
+        except Exception:
+            pass
+    return {}
+
+
+def run_b200(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from ska_pst_dsp_model_b200 import ops
+    from ska_pst_dsp_model_b200.filters import load_pst_taps
+    from ska_pst_dsp_model_b200.sharding import ShardedRoundTrip, plan_time_shards
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+                   "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 1000), __file__] + sys.argv[1:]
+            return subprocess.call(cmd)
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    log2n = args.log2_samples
+    n_global = world << log2n
+    taps = load_pst_taps(normalise=True)
+    shard = plan_time_shards(n_global, world, NCHAN, OS, 3072, NFFT, OVERLAP)[rank]
+    rt = ShardedRoundTrip(shard, NCHAN, OS, taps, NFFT, OVERLAP, "tukey", True, NPOL, torch.complex64, dev)
+    rt.load_owned(synth_torch(shard.own0, shard.own_n, NPOL, dev))
+    samples_rank = shard.own_n * NPOL
+    osf = 4.0 / 3.0
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        rt.step()
+    barrier()
+
+    # ---- timed region: K steps, device-resident input --------------------
+    K = args.steps
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K)]
+    rt.inverse.set_profiling(True)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    launches0 = ops.launch_count()
+    barrier()
+    t_begin = time.perf_counter()
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
+    for i in range(K):
+        ev[i][0].record()
+        from ska_pst_dsp_model_b200.sharding import exchange_halo
+        exchange_halo(torch.view_as_real(rt.local), shard)
+        rt.analysis.segment(rt.local, shard.own0, shard.fine0, shard.fine_n, out=rt.chan)
+        ev[i][1].record()
+        rt.inverse(rt.chan, out=rt.out)
+        ev[i][2].record()
+    end.record()
+    barrier()
+    t_end = time.perf_counter()
+    launches = ops.launch_count() - launches0
+    ms_total = start.elapsed_time(end)
+    prof = rt.inverse.get_profile()
+    rt.inverse.set_profiling(False)
+    clocks = sampler.stop(t_begin, t_end) if rank == 0 else None
+    ms_step = ms_total / K
+    t = torch.tensor([ms_step], dtype=torch.float64, device=dev)
+    tot = torch.tensor([float(samples_rank)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    ms_step = float(t.item())
+    total_samples = float(tot.item())
+    value = total_samples / (ms_step * 1e-3) / 1e6
+
+    ms_analysis = sum(e[0].elapsed_time(e[1]) for e in ev) / K
+    ms_inverse = sum(e[1].elapsed_time(e[2]) for e in ev) / K
+
+    # ---- per-kernel roofline (algorithmic bytes = the kernel's compulsory I/O) -
+    cb = 8  # complex64
+    bytes_analysis = (shard.need_n * NPOL + shard.fine_n * NCHAN * NPOL) * cb
+    bytes_chan = 2 * shard.fine_n * NCHAN * NPOL * cb
+    bytes_resample = (shard.fine_n * NCHAN * NPOL + shard.out_n * NPOL) * cb
+    n0, n1 = max(prof["chan_idft"][1], 1), max(prof["resample"][1], 1)
+    kernels = {
+        "pfb_analysis": {"ms_per_step": ms_analysis, "launches_per_step": 1, "bytes_per_step": bytes_analysis},
+        "pfb_chan_idft": {"ms_per_step": prof["chan_idft"][0] / K, "launches_per_step": n0 / K, "bytes_per_step": bytes_chan},
+        "pfb_resample": {"ms_per_step": prof["resample"][0] / K, "launches_per_step": n1 / K, "bytes_per_step": bytes_resample},
+    }
+    peak, peak_src = load_peak()
+    for kk in kernels.values():
+        kk["gbs"] = kk["bytes_per_step"] / (kk["ms_per_step"] * 1e-3) / 1e9 if kk["ms_per_step"] > 0 else None
+        kk["frac"] = kk["gbs"] / peak if kk["gbs"] else None
+    dom = max(kernels, key=lambda k: kernels[k]["ms_per_step"])
+    dk = kernels[dom]
+    traffic = load_traffic().get(dom)
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": dk["gbs"], "peak": peak, "unit": "GB/s",
+                "frac": dk["frac"], "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": dk["bytes_per_step"] / dk["launches_per_step"],
+                "avg_launch_ms": dk["ms_per_step"] / dk["launches_per_step"]}
+    e2e_bytes = 16 * (1 + osf) * (samples_rank)       # round trip with materialised channels
+    pipeline = {"algorithmic_bytes_per_step": e2e_bytes, "gbs": e2e_bytes / (ms_step * 1e-3) / 1e9,
+                "frac": e2e_bytes / (ms_step * 1e-3) / 1e9 / peak, "ms_analysis": ms_analysis, "ms_inversion": ms_inverse}
+
+    # ---- e2e: pinned host buffers through the public operators ------------
+    Ke = max(1, min(K, args.e2e_steps))
+    x_host = torch.empty((shard.own_n, NPOL), dtype=torch.complex64).pin_memory()
+    x_host.copy_(rt.local[: shard.own_n])
+    y_host = torch.empty((shard.out_n, NPOL), dtype=torch.complex64).pin_memory()
+
+    def e2e_step():
+        rt.local[: shard.own_n].copy_(x_host, non_blocking=True)
+        rt.step()
+        y_host.copy_(rt.out, non_blocking=True)
+
+    e2e_step()
+    barrier()
+    s2, e2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s2.record()
+    for _ in range(Ke):
+        e2e_step()
+    e2.record()
+    barrier()
+    ms_e2e = s2.elapsed_time(e2) / Ke
+    t = torch.tensor([ms_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_e2e = float(t.item())
+    e2e = {"value": total_samples / (ms_e2e * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": ms_e2e,
+           "h2d_bytes_per_step": shard.own_n * NPOL * cb, "d2h_bytes_per_step": shard.out_n * NPOL * cb,
+           "api": "sharding.ShardedRoundTrip.step() = ops.AnalysisPlan.segment + ops.InversePlan.__call__ over the C ABI"}
+
+    # quick in-bench sanity check of the result against the input (not the oracle):
+    # the round trip reproduces the delayed input (unity gain, deripple on)
+    y = rt.out[:4096, 0]
+    delay = 3072 // 2 + 36 * 256            # chop.m:36-37 with (dir,kludge) = (-1, 1)
+    xin = rt.local[delay: delay + 4096, 0] if shard.rank == 0 else None
+    rt_err = float((y - xin).abs().max() / xin.abs().max()) if xin is not None else None
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        workers = min(os.cpu_count() or 1, 64)
+        pool, jobs, samples = cpu_round_trip_setup(args.cpu_log2_samples, workers)
+        pool.map(_cpu_worker, jobs[: workers])               # warm the pool
+        t0 = time.perf_counter()
+        reps = 0
+        while reps < 2 or time.perf_counter() - t0 < 5.0:
+            pool.map(_cpu_worker, jobs)
+            reps += 1
+        dt = (time.perf_counter() - t0) / reps
+        pool.close()
+        # parity spot check of the GPU result against the oracle on the common prefix
+        ref = np.frombuffer(_CPU["out"], dtype=np.complex64).reshape(-1, NPOL)
+        m = min(ref.shape[0], 65536)
+        got = rt.out[:m].cpu().numpy()
+        perr = float(np.abs(got - ref[:m]).max() / np.abs(ref[:m]).max())
+        cpu_baseline = {"value": samples / dt / 1e6, "unit": UNIT, "cores": workers, "kind": "port",
+                        "sample": f"first 2^{args.cpu_log2_samples} samples/pol x {NPOL} pol of the same stream, "
+                                  f"{reps} repetitions, {len(jobs)} segments over {workers} processes",
+                        "parity_vs_gpu_prefix": perr}
+
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank != 0:
+        return 0
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": workload_config(log2n, world), "clocks": clocks, "e2e": e2e,
+        "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline, "kernels": kernels,
+        "pipeline": pipeline, "round_trip_max_err": rt_err,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--log2-samples", type=int, default=24, help="samples per pol per GPU (default 2^24)")
+    ap.add_argument("--cpu-log2-samples", type=int, default=22, help="bounded CPU sample per pol")
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_b200(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -92,6 +92,13 @@ int pfb_inverse_set_scratch_bytes(pfb_inverse_plan* plan, long long bytes);
 int pfb_inverse_execute_stage(pfb_inverse_plan* plan, int stage, const void* in_dev, void* out_dev,
                               int npol, long long n_dat, void* stream);
 
+/* per-kernel device timing of the inversion chain (CUDA events recorded around every
+ * launch on the caller's stream).  get_profile synchronises on the recorded events,
+ * returns summed milliseconds and launch counts for stage 0 (channel IDFT) and
+ * stage 1 (resampling) since the last call, and resets the counters. */
+int pfb_inverse_set_profiling(pfb_inverse_plan* plan, int on);
+int pfb_inverse_get_profile(pfb_inverse_plan* plan, double* ms2, long long* launches2);
+
 /* kernels launched by this library since load (bench.py "gpu_launches") */
 long long pfb_launch_count(void);
 

@@ -201,7 +201,8 @@ def _analysis_core(x1d, f, block, step, nblocks, start0, rot_extra, scale, cdt, 
         y = (fr * f).reshape(kb, phases, block).sum(axis=1)          # polyphase arms
         sp = np.fft.fft(y, axis=1)
         t0 = (start0 + (k0 + np.arange(kb, dtype=np.int64)) * step + rot_extra) % block
-        ph = np.exp(-2j * np.pi * np.outer(t0, np.arange(block)) / block)
+        ut, inv = np.unique(t0, return_inverse=True)     # only nu distinct rotations occur
+        ph = np.exp(-2j * np.pi * np.outer(ut, np.arange(block)) / block)[inv]
         out[:, k0:k0 + kb] = (scale * sp * ph).T.astype(cdt)
     return out
 

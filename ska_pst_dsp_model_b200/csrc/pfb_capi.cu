@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/pfb_b200.h"
@@ -161,8 +162,30 @@ struct pfb_inverse_plan {
   void* d_scratch = nullptr;
   size_t scratch_cap = 0;
   DeviceTables tabs;
+  // optional per-kernel timing (pfb_inverse_set_profiling): event pairs per stage
+  bool profiling = false;
+  std::vector<cudaEvent_t> ev_pool;
+  std::vector<std::pair<int, int>> ev_used[2];   // (start, stop) indices into ev_pool
+  size_t ev_next = 0;
+  int prof_begin(int stage, cudaStream_t st) {
+    if (!profiling) return -1;
+    while (ev_pool.size() < ev_next + 2) {
+      cudaEvent_t e;
+      if (cudaEventCreate(&e) != cudaSuccess) return -1;
+      ev_pool.push_back(e);
+    }
+    const int a = (int)ev_next, b = (int)ev_next + 1;
+    ev_next += 2;
+    ev_used[stage].push_back({a, b});
+    cudaEventRecord(ev_pool[a], st);
+    return b;
+  }
+  void prof_end(int tok, cudaStream_t st) {
+    if (tok >= 0) cudaEventRecord(ev_pool[tok], st);
+  }
   ~pfb_inverse_plan() {
     if (d_scratch) cudaFree(d_scratch);
+    for (cudaEvent_t e : ev_pool) cudaEventDestroy(e);
   }
 };
 
@@ -428,11 +451,12 @@ int pfb_inverse_set_scratch_bytes(pfb_inverse_plan* p, long long bytes) {
 template <typename T>
 static int launch_chan_idft(pfb_inverse_plan* p, const void* in, void* out, int npol, long long nrows, cudaStream_t st) {
   if (nrows <= 0) return PFB_OK;
+  const int tok = p->prof_begin(0, st);
   if (p->low_fast) {
     bool done = false;
     int rc = low_chan_idft_launch<T>(p->d_low, in, out, npol, nrows, st, &done);
     if (rc) return fail(PFB_ERR_CUDA, "pfb_chan_idft_low launch: %s", cudaGetErrorString((cudaError_t)rc));
-    if (done) return check_launch("pfb_chan_idft_low");
+    if (done) { p->prof_end(tok, st); return check_launch("pfb_chan_idft_low"); }
   }
   ChanIdftArgs a;
   memset(&a, 0, sizeof(a));
@@ -446,17 +470,19 @@ static int launch_chan_idft(pfb_inverse_plan* p, const void* in, void* out, int 
   const long long grid = (nrows + rb - 1) / rb;
   if (grid > 2147483647ll) return fail(PFB_ERR_ARG, "too many rows for one launch");
   pfb_chan_idft_generic<T><<<(unsigned)grid, 256, smem, st>>>(a);
+  p->prof_end(tok, st);
   return check_launch("pfb_chan_idft_generic");
 }
 
 template <typename T>
 static int launch_resample(pfb_inverse_plan* p, const void* v, void* out, int npol, long long nblk, cudaStream_t st) {
   if (nblk <= 0) return PFB_OK;
+  const int tok = p->prof_begin(1, st);
   if (p->low_fast) {
     bool done = false;
     int rc = low_resample_launch<T>(p->d_low, v, out, npol, nblk, st, &done);
     if (rc) return fail(PFB_ERR_CUDA, "pfb_resample_low launch: %s", cudaGetErrorString((cudaError_t)rc));
-    if (done) return check_launch("pfb_resample_low");
+    if (done) { p->prof_end(tok, st); return check_launch("pfb_resample_low"); }
   }
   ResampleArgs a;
   memset(&a, 0, sizeof(a));
@@ -486,6 +512,7 @@ static int launch_resample(pfb_inverse_plan* p, const void* v, void* out, int np
     if (rc) return rc;
     done += nb;
   }
+  p->prof_end(tok, st);
   return PFB_OK;
 }
 
@@ -515,6 +542,30 @@ static int inverse_run(pfb_inverse_plan* p, const void* in, void* out, int npol,
     rc = launch_resample<T>(p, p->d_scratch, dst, npol, nb, st);
     if (rc) return rc;
   }
+  return PFB_OK;
+}
+
+int pfb_inverse_set_profiling(pfb_inverse_plan* p, int on) {
+  if (!p) return fail(PFB_ERR_ARG, "null plan");
+  p->profiling = on != 0;
+  p->ev_used[0].clear(); p->ev_used[1].clear(); p->ev_next = 0;
+  return PFB_OK;
+}
+
+int pfb_inverse_get_profile(pfb_inverse_plan* p, double* ms, long long* launches) {
+  if (!p || !ms || !launches) return fail(PFB_ERR_ARG, "null pointer");
+  CU(cudaSetDevice(p->device));
+  for (int s = 0; s < 2; ++s) {
+    ms[s] = 0; launches[s] = (long long)p->ev_used[s].size();
+    for (auto& pr : p->ev_used[s]) {
+      CU(cudaEventSynchronize(p->ev_pool[pr.second]));
+      float t = 0;
+      CU(cudaEventElapsedTime(&t, p->ev_pool[pr.first], p->ev_pool[pr.second]));
+      ms[s] += t;
+    }
+    p->ev_used[s].clear();
+  }
+  p->ev_next = 0;
   return PFB_OK;
 }
 

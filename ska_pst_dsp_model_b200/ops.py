@@ -168,6 +168,16 @@ class InversePlan:
                                                 _stream_ptr(self.device)))
         return out
 
+    def set_profiling(self, on=True):
+        _l.check(_l.lib.pfb_inverse_set_profiling(self._h, int(on)))
+
+    def get_profile(self):
+        """{'chan_idft': (ms, launches), 'resample': (ms, launches)} since the last call."""
+        ms = (ctypes.c_double * 2)()
+        n = (ctypes.c_longlong * 2)()
+        _l.check(_l.lib.pfb_inverse_get_profile(self._h, ms, n))
+        return {"chan_idft": (ms[0], n[0]), "resample": (ms[1], n[1])}
+
     def stage(self, stage, x, out):
         n_dat, nchan, npol = x.shape
         with torch.cuda.device(self.device):
