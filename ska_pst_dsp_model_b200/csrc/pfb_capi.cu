@@ -238,7 +238,8 @@ int pfb_analysis_plan_create(pfb_analysis_plan** plan, int variant, int nchan, i
   }
   int rc = dtype == PFB_DTYPE_C64 ? analysis_build<float>(p, taps) : analysis_build<double>(p, taps);
   if (rc == PFB_OK && variant != PFB_VARIANT_PADDED)
-    rc = low_analysis_plan_init(p->N, p->nu, p->de, p->P, p->dtype, taps, p->ntaps, &p->tabs.ptrs, &p->d_low_taps, &p->low_fast);
+    rc = low_analysis_plan_init(p->N, p->nu, p->de, p->P, p->dtype, taps, p->ntaps, p->scale, &p->tabs.ptrs, &p->d_low_taps, &p->low_fast);
+  if (rc > 0) rc = fail(PFB_ERR_CUDA, "fast-path table upload: %s", cudaGetErrorString((cudaError_t)rc));
   if (rc) { delete p; return rc; }
   *plan = p;
   return PFB_OK;
@@ -261,14 +262,11 @@ long long pfb_analysis_nblocks(const pfb_analysis_plan* p, long long n_dat, int 
 
 int pfb_analysis_nchan_out(const pfb_analysis_plan* p) { return p ? p->nchan_out : PFB_ERR_ARG; }
 
-template <typename T> static int analysis_launch(pfb_analysis_plan* p, AnalysisArgs& a, cudaStream_t st) {
-  if (a.nblocks <= 0) return PFB_OK;
-  if (p->low_fast) {
-    bool done = false;
-    int rc = low_analysis_launch<T>(a, p->d_low_taps, st, &done);
-    if (rc) return fail(PFB_ERR_CUDA, "pfb_analysis_low launch: %s", cudaGetErrorString((cudaError_t)rc));
-    if (done) return check_launch("pfb_analysis_low");
-  }
+template <typename T> static int analysis_launch_generic(AnalysisArgs a, long long b0, long long b1, cudaStream_t st) {
+  if (b1 <= b0) return PFB_OK;
+  a.start0 += b0 * (long long)a.S;
+  a.kout0 += b0;
+  a.nblocks = b1 - b0;
   const int ld = padded_len<T>(a.N);
   int kb = 4096 / (a.N * a.npol);
   if (kb < 1) kb = 1;
@@ -280,6 +278,24 @@ template <typename T> static int analysis_launch(pfb_analysis_plan* p, AnalysisA
   if (grid > 2147483647ll) return fail(PFB_ERR_ARG, "too many blocks for one launch");
   pfb_analysis_generic<T><<<(unsigned)grid, 256, smem, st>>>(a);
   return check_launch("pfb_analysis_generic");
+}
+
+template <typename T> static int analysis_launch(pfb_analysis_plan* p, AnalysisArgs& a, cudaStream_t st) {
+  if (a.nblocks <= 0) return PFB_OK;
+  long long k_lo = 0, k_hi = 0;
+  if (p->low_fast) {
+    int rc = low_analysis_launch<T>(a, p->d_low_taps, st, &k_lo, &k_hi);
+    if (rc) return fail(PFB_ERR_CUDA, "pfb_analysis_low launch: %s", cudaGetErrorString((cudaError_t)rc));
+    if (k_hi > k_lo) {
+      rc = check_launch("pfb_analysis_low");
+      if (rc) return rc;
+    }
+  }
+  if (k_hi <= k_lo) return analysis_launch_generic<T>(a, 0, a.nblocks, st);
+  // head / tail blocks whose window leaves the resident samples (zero fill) stay on the generic kernel
+  int rc = analysis_launch_generic<T>(a, 0, k_lo, st);
+  if (rc) return rc;
+  return analysis_launch_generic<T>(a, k_hi, a.nblocks, st);
 }
 
 static int analysis_run(pfb_analysis_plan* p, const void* in, long long n_local, long long sample0, void* out,
@@ -392,8 +408,10 @@ static int inverse_build(pfb_inverse_plan* p, const double* taper, const double*
     if ((rc = p->tabs.upload(jm, &djm))) return rc;
     p->d_jmap = djm;
   }
-  return low_inverse_plan_init<T>(p->nchan, p->nu, p->de, p->Nf, p->ov, p->spans, p->combine, tp, w, g,
-                                  &p->tabs.ptrs, &p->d_low, &p->low_fast);
+  rc = low_inverse_plan_init<T>(p->nchan, p->nu, p->de, p->Nf, p->ov, p->spans, p->combine, tp, p->d_wt,
+                                &p->tabs.ptrs, &p->d_low, &p->low_fast);
+  if (rc > 0) return fail(PFB_ERR_CUDA, "fast-path table upload: %s", cudaGetErrorString((cudaError_t)rc));
+  return rc;
 }
 
 int pfb_inverse_plan_create(pfb_inverse_plan** plan, int nchan, int os_nu, int os_de, int nfft, int overlap,

@@ -1,28 +1,637 @@
-// Shape-specialised fast kernels (SKA-Low: 256 channels, OS 4/3, 12 taps/arm;
-// inversion Nf=256 -> FN_width=192).  Selected by the plan when the shape matches.
+// Shape-specialised fast kernels for the SKA-Low PST shape (fp32):
+//   K1  pfb_analysis_low  : 256 channels, OS 4/3 (step 192), 12 taps/arm (3072-tap filter)
+//   K2  pfb_chan_idft_low : 256-point inverse DFT across channels
+//   K3  pfb_resample_low  : Nf=256 -> FN_width=192 overlap-save resampling per column
+// Selected by the plan when the shape matches; anything else runs pfb_generic.cuh.
+//
+// Design notes (DESIGN.md has the derivations):
+//  * K1 exploits gcd(step, N) = 64: input samples with index == r (mod 64) only ever
+//    meet taps with index == r (mod 64).  One thread owns one residue class (and one
+//    polarisation): its 48 taps stay in registers for the whole launch, and a 48-sample
+//    sliding window of its class stream lives in registers too, advancing 3 samples per
+//    output block.  Every input sample is read from shared memory exactly once and used
+//    in 16 complex MACs; the window rotation is resolved statically by unrolling 16 blocks.
+//    The 4 arms a thread produces are exactly the inputs of one radix-4 DIF butterfly of
+//    the 256-point FFT, and the oversampling phase rotation (a multiple of 64 slots) is a
+//    static renaming of those 4 registers.  The remaining 64-point FFTs run one per thread,
+//    entirely in registers, after one exchange through shared memory.
+//  * input is streamed by the TMA bulk-copy engine (cp.async.bulk + mbarrier) into a
+//    3-stage shared-memory ring; outputs go straight from registers to global memory in
+//    fully used 32-byte sectors.
+//  * K2/K3 split the 256-point FFT 16 x 16 (and the 192-point inverse 12 x 16) over 16
+//    lanes per transform with in-register radix-16/12 butterflies and compile-time twiddles.
 #pragma once
 #include <vector>
+
 #include "pfb_generic.cuh"
+#include "twiddle_tables.cuh"
 
 namespace pfb {
+namespace low {
 
-inline int low_analysis_plan_init(int N, int nu, int de, int P, int dtype, const double* taps, int ntaps,
+typedef Cx<float> C;
+#ifndef K1VAR
+#define K1VAR 0
+#endif
+
+// a * exp(DIR * 2 pi i k / N), k known after unrolling
+template <int N, int DIR> __device__ __forceinline__ C mul_lit(C a, int k) {
+  k %= N;
+  if (k == 0) return a;
+  if (2 * k == N) return mk<float>(-a.x, -a.y);
+  if (4 * k == N) return mul_i<DIR>(a);
+  if (4 * k == 3 * N) return mul_i<-DIR>(a);
+  const float c = TwLit<N>::c(k), s = DIR * TwLit<N>::s(k);
+  return mk<float>(a.x * c - a.y * s, a.x * s + a.y * c);
+}
+
+// Two-pass DIF FFT of N1*N2 points held in registers.  X[k] ends at slot
+// N2*(k % N1) + k / N1  (see slot()).
+template <int N1, int N2, int DIR> __device__ __forceinline__ void fft_reg(C* a) {
+  constexpr int N = N1 * N2;
+#pragma unroll
+  for (int q = 0; q < N2; ++q) {
+    C t[N1];
+#pragma unroll
+    for (int i = 0; i < N1; ++i) t[i] = a[q + N2 * i];
+    Dft<N1, DIR, float>::run(t);
+#pragma unroll
+    for (int o = 0; o < N1; ++o) a[q + N2 * o] = mul_lit<N, DIR>(t[o], q * o);
+  }
+#pragma unroll
+  for (int o = 0; o < N1; ++o) Dft<N2, DIR, float>::run(a + N2 * o);
+}
+template <int N1, int N2> __host__ __device__ constexpr int slot(int k) { return N2 * (k % N1) + k / N1; }
+
+__device__ __forceinline__ C ld_nc(const C* p) {
+  float2 v = __ldg(reinterpret_cast<const float2*>(p));
+  return mk<float>(v.x, v.y);
+}
+__device__ __forceinline__ void st_cs(C* p, C v) {   // streaming store (written once, read by a later kernel)
+  __stcs(reinterpret_cast<float2*>(p), make_float2(v.x, v.y));
+}
+
+// ---- mbarrier / TMA bulk copy helpers --------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// ===========================================================================
+// K1: analysis
+// ===========================================================================
+struct AnaArgs {
+  const C* in;           // [t][pol]
+  C* out;                // [k][chan][pol]
+  const float* taps;     // [48][64]: taps[u][r] = scale * f[r + 64 u]
+  const float2* tw;      // [3][64]:  exp(-2 pi i r o / 256), o = 1..3
+  long long s0;          // window start of block 0 (>= 0, rotation-free: (phase0+s0) % 256 == 0)
+  long long n_local;     // samples resident in `in`
+  long long nblk;        // blocks to produce
+  long long kout0;       // first output block slot
+  int L;                 // blocks per CTA (multiple of 16)
+  int chan_first, nchan_out;
+};
+
+constexpr int kAnaStages = 3;
+constexpr int kTileBlocks = 4;                 // output blocks fed by one TMA tile
+constexpr int kTileSamples = kTileBlocks * 192;
+constexpr int kExStride = 65;                  // odd: conflict-free per-task rows
+
+template <int NPOL> constexpr size_t ana_smem_bytes() {
+  return (size_t)kAnaStages * kTileSamples * NPOL * sizeof(C) + (size_t)64 * NPOL * kExStride * sizeof(C) + 64;
+}
+
+template <int NPOL>
+__global__ void __launch_bounds__(64 * NPOL, NPOL == 2 ? 2 : 4) pfb_analysis_low(const AnaArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  C* ring = reinterpret_cast<C*>(smem_raw);                                  // [stage][768][NPOL]
+  C* ex = ring + kAnaStages * kTileSamples * NPOL;                           // [64*NPOL tasks][65]
+  uint64_t* full = reinterpret_cast<uint64_t*>(ex + 64 * NPOL * kExStride);  // [stages]
+  uint64_t* empty = full + kAnaStages;
+
+  const int tid = threadIdx.x;
+  const int r = tid / NPOL, pol = tid % NPOL;
+  const int lane = tid & 31;
+  const long long kA = (long long)blockIdx.x * a.L;
+  const long long kend = min(kA + (long long)a.L, a.nblk);
+  const int niter = (int)((kend - kA + 15) / 16);
+  const int ntiles = niter * 4;
+  constexpr uint32_t kTileBytes = kTileSamples * NPOL * sizeof(C);
+  const long long tile0 = a.s0 + 192 * kA + 2880;       // first sample of tile 0
+  const long long total_bytes = a.n_local * NPOL * (long long)sizeof(C);
+
+  auto issue_tile = [&](int i) {
+    const long long b0 = (tile0 + (long long)i * kTileSamples) * NPOL * (long long)sizeof(C);
+    long long nbytes = total_bytes - b0;
+    if (nbytes > (long long)kTileBytes) nbytes = kTileBytes;
+    uint64_t* bar = &full[i % kAnaStages];
+    if (nbytes > 0) {
+      mbar_expect_tx(bar, (uint32_t)nbytes);
+      tma_load_1d(ring + (size_t)(i % kAnaStages) * kTileSamples * NPOL, reinterpret_cast<const char*>(a.in) + b0,
+                  (uint32_t)nbytes, bar);
+    } else {
+      mbar_arrive(bar);
+    }
+  };
+
+  if (tid == 0) {
+    for (int s = 0; s < kAnaStages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 2 * NPOL);   // one arrive per warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid == 0)
+    for (int i = 0; i < kAnaStages && i < ntiles; ++i) issue_tile(i);
+
+  // taps and first-stage twiddles of this residue class: registers for the whole launch
+  float tap[48];
+#pragma unroll
+  for (int u = 0; u < 48; ++u) tap[u] = __ldg(a.taps + u * 64 + r);
+  C tw[3];
+#pragma unroll
+  for (int o = 0; o < 3; ++o) {
+    float2 v = __ldg(a.tw + o * 64 + r);
+    tw[o] = mk<float>(v.x, v.y);
+  }
+  // window prologue: elements 0..44 of block kA's window straight from global
+  C w[48];
+  {
+    const C* p = a.in + (a.s0 + 192 * kA + r) * NPOL + pol;
+#pragma unroll
+    for (int u = 0; u < 45; ++u) w[u] = ld_nc(p + (long long)u * 64 * NPOL);
+  }
+
+  for (int it = 0; it < niter; ++it) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int tile = it * 4 + (j >> 2);
+      if ((j & 3) == 0) {
+        if (tid == 0 && tile >= 1 && tile - 1 + kAnaStages < ntiles) {
+          // refill the stage freed by the previous tile
+          mbar_wait(&empty[(tile - 1) % kAnaStages], ((tile - 1) / kAnaStages) & 1);
+          issue_tile(tile - 1 + kAnaStages);
+        }
+        mbar_wait(&full[tile % kAnaStages], (tile / kAnaStages) & 1);
+      }
+      // the 3 new samples of this block: window elements 45..47
+      {
+        const C* sp = ring + ((size_t)(tile % kAnaStages) * kTileSamples + (j & 3) * 192 + r) * NPOL + pol;
+#pragma unroll
+        for (int e = 0; e < 3; ++e) w[(3 * j + 45 + e) % 48] = sp[e * 64 * NPOL];
+      }
+      if ((j & 3) == 3) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[tile % kAnaStages]);
+      }
+      // polyphase arms: acc[a] = sum_m tap[a+4m] * window[a+4m]
+      C acc[4];
+#pragma unroll
+      for (int ar = 0; ar < 4; ++ar) {
+        float sx = 0.f, sy = 0.f;
+#pragma unroll
+        for (int m = 0; m < 12; ++m) {
+          const int u = ar + 4 * m;
+          const C v = w[(3 * j + u) % 48];
+          sx = fmaf(tap[u], v.x, sx);
+          sy = fmaf(tap[u], v.y, sy);
+        }
+        acc[ar] = mk<float>(sx, sy);
+      }
+      // phase rotation: arm ar feeds FFT slot r + 64*((ar + 3j) mod 4)  ->  z[i] = acc[(i + j) mod 4]
+      C z[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) z[i] = acc[(i + j) & 3];
+      Dft<4, -1, float>::run(z);
+      z[1] = z[1] * tw[0];
+      z[2] = z[2] * tw[1];
+      z[3] = z[3] * tw[2];
+#pragma unroll
+      for (int o = 0; o < 4; ++o) ex[(size_t)((j * NPOL + pol) * 4 + o) * kExStride + r] = z[o];
+    }
+    __syncthreads();
+#if K1VAR != 1
+    {
+      // one 64-point FFT per thread (task = block j, pol, o), two radix-8 passes over the
+      // thread's private row in shared memory (the 48-sample window keeps the registers)
+      const int o = tid & 3, tp = (tid >> 2) % NPOL, tj = tid / (4 * NPOL);
+      C* row = ex + (size_t)tid * kExStride;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        C t[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t[i] = row[q + 8 * i];
+        Dft<8, -1, float>::run(t);
+#pragma unroll
+        for (int oo = 0; oo < 8; ++oo) row[q + 8 * oo] = mul_lit<64, -1>(t[oo], q * oo);
+        if (q & 1) asm volatile("" ::: "memory");   // keep at most two butterflies in flight (register budget)
+      }
+      const long long kb = kA + 16ll * it + tj;
+      C* op = a.out + ((a.kout0 + kb) * a.nchan_out) * NPOL + tp;
+      const bool live = kb < kend;
+#pragma unroll
+      for (int o1 = 0; o1 < 8; ++o1) {
+        C t[8];
+#pragma unroll
+        for (int qq = 0; qq < 8; ++qq) t[qq] = row[8 * o1 + qq];
+        Dft<8, -1, float>::run(t);
+#pragma unroll
+        for (int o2 = 0; o2 < 8; ++o2) {
+          const int c = o + 4 * (o1 + 8 * o2);       // X256[o + 4 k'], k' = o1 + 8 o2
+          const int ci = (c - a.chan_first) & 255;
+          if (live && ci < a.nchan_out) op[(long long)ci * NPOL] = t[o2];
+        }
+        if (o1 & 1) asm volatile("" ::: "memory");
+      }
+    }
+#endif
+    __syncthreads();
+  }
+}
+
+// ===========================================================================
+// K2: 256-point inverse DFT across channels, 16 lanes x 16 points
+// ===========================================================================
+struct ChanArgs {
+  const C* in;          // [row][256][pol]
+  C* out;               // [row][256][pol]
+  const float2* tw256;  // [256] exp(-2 pi i k/256)
+  long long nrows;
+};
+
+constexpr int kColStride = 273;   // 16*17 + 1, odd
+constexpr int kQStride = 17;
+
+template <int NPOL>
+__global__ void __launch_bounds__(256, 3) pfb_chan_idft_low(const ChanArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  C* ex = reinterpret_cast<C*>(smem_raw);    // [2][16 ffts][273]
+  const int tid = threadIdx.x;
+  // lanes: (q, pol) contiguous in memory; 16 FFTs per CTA pass = 16/NPOL rows
+  const int lane32 = tid & 31, grp = tid >> 5;       // 8 groups of 32 lanes
+  int q, pol, rsub;
+  if (NPOL == 2) { q = lane32 >> 1; pol = lane32 & 1; rsub = grp; }
+  else { q = lane32 & 15; pol = 0; rsub = grp * 2 + (lane32 >> 4); }
+  constexpr int ROWS = 16 / NPOL;
+  const int fft = rsub * NPOL + pol;
+  C tw[15];
+#pragma unroll
+  for (int o = 1; o < 16; ++o) {
+    float2 v = __ldg(a.tw256 + ((q * o) & 255));
+    tw[o - 1] = mk<float>(v.x, -v.y);          // inverse: conj
+  }
+  const long long npass = (a.nrows + ROWS - 1) / ROWS;
+  int buf = 0;
+  for (long long ps = blockIdx.x; ps < npass; ps += gridDim.x, buf ^= 1) {
+    const long long row = ps * ROWS + rsub;
+    C* e = ex + (size_t)buf * 16 * kColStride + (size_t)fft * kColStride;
+    C x[16];
+    if (row < a.nrows) {
+      const C* p = a.in + (row * 256 + q) * NPOL + pol;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) x[i] = ld_nc(p + i * 16 * NPOL);
+      fft_reg<4, 4, +1>(x);
+#pragma unroll
+      for (int o = 0; o < 16; ++o) {
+        C v = x[slot<4, 4>(o)];
+        if (o) v = v * tw[o - 1];
+        e[o * kQStride + q] = v;
+      }
+    }
+    __syncthreads();
+    if (row < a.nrows) {
+      const int o = q;   // second pass: this lane owns output residue o
+#pragma unroll
+      for (int i = 0; i < 16; ++i) x[i] = e[o * kQStride + i];
+      fft_reg<4, 4, +1>(x);
+      C* p = a.out + (row * 256 + o) * NPOL + pol;
+#pragma unroll
+      for (int o2 = 0; o2 < 16; ++o2) p[o2 * 16 * NPOL] = x[slot<4, 4>(o2)];
+    }
+  }
+}
+
+// ===========================================================================
+// K3: per column: taper -> FFT256 -> keep 192 bins x weights -> IFFT192 -> keep middle
+// ===========================================================================
+struct ResArgs {
+  const C* v;           // [tau][nchan][pol]
+  C* out;               // [T2][nchan][pol]
+  const float* taper;   // [256]
+  const C* wt;          // [nchan][192] in FN order (r)
+  const float2* tw256;  // [256] exp(-2 pi i k/256)
+  const float2* tw192;  // [192] exp(+2 pi i k/192)
+  int nchan, keep, ov2, keep2, flip;   // flip: critical sampling => y *= (-1)^t2
+  int nblk;             // overlap-save blocks in this launch
+  int nsplit;           // CTAs per column group along n
+};
+
+template <int NPOL> constexpr size_t res_smem_bytes() {
+  return (size_t)2 * 16 * kColStride * sizeof(C) + (size_t)16 * 193 * sizeof(C) + 256 * sizeof(float);
+}
+
+template <int NPOL>
+__global__ void __launch_bounds__(256, 2) pfb_resample_low(const ResArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  C* exA = reinterpret_cast<C*>(smem_raw);            // [16 cols][273]  phase 1 -> 2
+  C* exB = exA + 16 * kColStride;                     // [16 cols][273]  phase 2 -> 3 ([m][o] stride 17)
+  C* swt = exB + 16 * kColStride;                     // [16 cols][193]  weights of this column group
+  float* stp = reinterpret_cast<float*>(swt + 16 * 193);
+  const int tid = threadIdx.x;
+  const int c = tid & 15, q = tid >> 4;               // column, lane-in-transform
+  constexpr int T1G = 16 / NPOL;                      // t1 values per CTA
+  const int groups = a.nchan / T1G;
+  const int g = blockIdx.x % groups, sp = blockIdx.x / groups;
+  const int t1_0 = g * T1G;
+  const long long rowlen = (long long)a.nchan * NPOL;
+  const int per = (a.nblk + a.nsplit - 1) / a.nsplit;
+  const int n_begin = sp * per, n_end = min(a.nblk, n_begin + per);
+
+  for (int i = tid; i < 16 * 192; i += 256) {
+    const int cc = i / 192, rr = i % 192;
+    swt[cc * 193 + rr] = a.wt[(size_t)(t1_0 + cc / NPOL) * 192 + rr];
+  }
+  stp[tid] = a.taper[tid];
+  C tw1[15], tw2[11];
+#pragma unroll
+  for (int o = 1; o < 16; ++o) {
+    float2 v = __ldg(a.tw256 + ((q * o) & 255));
+    tw1[o - 1] = mk<float>(v.x, v.y);
+  }
+#pragma unroll
+  for (int m = 1; m < 12; ++m) {
+    float2 v = __ldg(a.tw192 + ((q * m) % 192));
+    tw2[m - 1] = mk<float>(v.x, v.y);
+  }
+  __syncthreads();
+
+  const C* vcol = a.v + (long long)t1_0 * NPOL + c;
+  C* ocol = a.out + (long long)t1_0 * NPOL + c;
+  C* eA = exA + c * kColStride;
+  C* eB = exB + c * kColStride;
+  const float sgn_odd = a.flip ? -1.f : 1.f;
+
+  for (int n = n_begin; n < n_end; ++n) {
+    C x[16];
+    {
+      // phase 1: lane q holds tau = q + 16 i
+      const C* p = vcol + ((long long)n * a.keep + q) * rowlen;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) x[i] = ld_nc(p + (long long)i * 16 * rowlen) * stp[q + 16 * i];
+      fft_reg<4, 4, -1>(x);
+#pragma unroll
+      for (int o = 0; o < 16; ++o) {
+        C v = x[slot<4, 4>(o)];
+        if (o) v = v * tw1[o - 1];
+        eA[o * kQStride + q] = v;
+      }
+    }
+    __syncthreads();
+    {
+      // phase 2: lane o=q: bins b = o + 16 o2; keep o2 in {0..5} U {10..15}
+      const int o = q;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) x[i] = eA[o * kQStride + i];
+      fft_reg<4, 4, -1>(x);
+      C z[12];
+#pragma unroll
+      for (int k = 0; k < 12; ++k) {
+        const int o2 = k < 6 ? k : k + 4;
+        const int b = o + 16 * o2;                        // FFT bin
+        const int rr = b < 96 ? b + 96 : b - 160;         // FN-order index of that bin
+        z[k] = x[slot<4, 4>(o2)] * swt[c * 193 + rr];
+      }
+      // z[k] sits at inverse-transform index i' = o + 16 k: 12-point inverse DFT over k
+      fft_reg<3, 4, +1>(z);
+#pragma unroll
+      for (int m = 0; m < 12; ++m) {
+        C v = z[slot<3, 4>(m)];
+        if (m) v = v * tw2[m - 1];                        // exp(+2 pi i o m / 192)
+        eB[m * kQStride + o] = v;
+      }
+    }
+    __syncthreads();
+    if (q < 12) {
+      // phase 3: lane m=q: y[m + 12 j] = sum_o eB[m][o] exp(+2 pi i o j / 16)
+      const int m = q;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) x[i] = eB[m * kQStride + i];
+      fft_reg<4, 4, +1>(x);
+      C* p = ocol + ((long long)n * a.keep2 - a.ov2 + m) * rowlen;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int t2 = m + 12 * j;
+        if (t2 >= a.ov2 && t2 < 192 - a.ov2) {
+          C v = x[slot<4, 4>(j)];
+          if ((t2 & 1) && a.flip) v = mk<float>(-v.x, -v.y);
+          p[(long long)(12 * j) * rowlen] = v;
+        }
+      }
+    }
+    (void)sgn_odd;
+  }
+}
+
+// ===========================================================================
+// host side
+// ===========================================================================
+struct LowInverse {
+  const float* taper;
+  const C* wt;
+  const float2* tw256;
+  const float2* tw192;
+  int nchan, keep, ov2, keep2, flip, chan_fast;
+};
+
+template <typename U> inline int upload_raw(const std::vector<U>& h, std::vector<void*>* allocs, const U** out) {
+  void* d = nullptr;
+  cudaError_t e = cudaMalloc(&d, h.size() * sizeof(U) + 16);
+  if (e != cudaSuccess) return (int)e;
+  allocs->push_back(d);
+  e = cudaMemcpy(d, h.data(), h.size() * sizeof(U), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) return (int)e;
+  *out = reinterpret_cast<const U*>(d);
+  return 0;
+}
+
+inline void unit_circle(long long m, long long n, int sign, double* c, double* s) {
+  m %= n;
+  if (m < 0) m += n;
+  const double ang = 2.0 * 3.14159265358979323846 * ((double)m / (double)n);
+  *c = cos(ang);
+  *s = sign * sin(ang);
+  if (m == 0) { *c = 1; *s = 0; }
+  else if (2 * m == n) { *c = -1; *s = 0; }
+  else if (4 * m == n) { *c = 0; *s = sign; }
+  else if (4 * m == 3 * n) { *c = 0; *s = -sign; }
+}
+
+inline std::vector<float2> unit_table(int n, int sign) {
+  std::vector<float2> t(n);
+  for (int k = 0; k < n; ++k) {
+    double c, s;
+    unit_circle(k, n, sign, &c, &s);
+    t[k] = make_float2((float)c, (float)s);
+  }
+  return t;
+}
+
+struct LowAnalysis {
+  const float* taps;
+  const float2* tw;
+};
+
+}  // namespace low
+
+// ---- analysis --------------------------------------------------------------
+inline int low_analysis_plan_init(int N, int nu, int de, int P, int dtype, const double* taps, int ntaps, double scale,
                                   std::vector<void*>* allocs, const void** d_low, bool* enabled) {
   *enabled = false;
+  if (!(N == 256 && nu == 4 && de == 3 && P == 12 && dtype == 0)) return 0;
+  std::vector<float> t(48 * 64, 0.f);
+  for (int u = 0; u < 48; ++u)
+    for (int r = 0; r < 64; ++r) {
+      const int n = r + 64 * u;
+      t[u * 64 + r] = n < ntaps ? (float)(scale * taps[n]) : 0.f;
+    }
+  std::vector<float2> tw(3 * 64);
+  for (int o = 1; o < 4; ++o)
+    for (int r = 0; r < 64; ++r) {
+      double c, s;
+      low::unit_circle((long long)r * o, 256, -1, &c, &s);
+      tw[(o - 1) * 64 + r] = make_float2((float)c, (float)s);
+    }
+  low::LowAnalysis* h = new low::LowAnalysis();
+  int rc = low::upload_raw(t, allocs, &h->taps);
+  if (!rc) rc = low::upload_raw(tw, allocs, &h->tw);
+  if (rc) { delete h; return rc; }
+  *d_low = h;   // small host struct, leaked with the plan (two pointers)
+  *enabled = true;
   return 0;
 }
 
+// returns a cudaError (0 ok); *nfast = number of leading-aligned blocks handled by the fast kernel,
+// the caller runs the generic kernel for blocks [0,*k_lo) and [*k_hi, nblocks)
 template <typename T>
-int low_analysis_launch(const AnalysisArgs& a, const void* d_low, cudaStream_t st, bool* done) {
-  *done = false;
+int low_analysis_launch(const AnalysisArgs& g, const void* d_low, cudaStream_t st, long long* k_lo, long long* k_hi) {
+  *k_lo = *k_hi = 0;
   return 0;
 }
 
+template <>
+inline int low_analysis_launch<float>(const AnalysisArgs& g, const void* d_low, cudaStream_t st, long long* k_lo,
+                                      long long* k_hi) {
+  *k_lo = *k_hi = 0;
+  const low::LowAnalysis* h = reinterpret_cast<const low::LowAnalysis*>(d_low);
+  if (g.kout_mod != 0) return 0;
+  // fast blocks: window fully resident and rotation-free block 0
+  // block k window = [start0 + 192k, start0 + 192k + 3072)
+  long long lo = 0;
+  if (g.start0 < 0) lo = (-g.start0 + 191) / 192;
+  // rotation of block lo must be 0 (mod 256) and lo a multiple of 4 keeps (3k mod 4) static
+  {
+    int tries = 0;
+    while (tries < 4 && (((g.phase0 + g.start0 + 192 * lo) % 256 + 256) % 256 != 0)) { ++lo; ++tries; }
+    if (tries == 4) return 0;
+  }
+  const long long n_eff = g.npol == 1 ? (g.n_dat & ~1ll) : g.n_dat;   // whole 16-byte units for the TMA
+  long long hi = (n_eff - 3072 - g.start0) / 192 + 1;        // blocks with window end <= n_dat
+  if (n_eff - 3072 - g.start0 < 0) hi = 0;
+  if (hi > g.nblocks) hi = g.nblocks;
+  if (hi - lo < 64) return 0;
+  const long long s0 = g.start0 + 192 * lo;
+  // TMA source alignment: 16 bytes
+  if (((uintptr_t)g.in + (uintptr_t)((s0 + 2880) * g.npol * 8)) % 16 != 0) return 0;
+  if (g.npol == 1 && (((uintptr_t)g.in) % 16 != 0 || (s0 % 2) != 0)) return 0;
+  const long long nblk = hi - lo;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const long long resident = (long long)sms * (g.npol == 2 ? 2 : 4);
+  long long waves = (nblk + resident * 512 - 1) / (resident * 512);
+  if (waves < 1) waves = 1;
+  long long L = (nblk + resident * waves - 1) / (resident * waves);
+  L = (L + 15) / 16 * 16;
+  if (L < 16) L = 16;
+  const long long grid = (nblk + L - 1) / L;
+  low::AnaArgs a;
+  a.in = reinterpret_cast<const low::C*>(g.in);
+  a.out = reinterpret_cast<low::C*>(g.out);
+  a.taps = h->taps; a.tw = h->tw;
+  a.s0 = s0; a.n_local = n_eff; a.nblk = nblk; a.kout0 = g.kout0 + lo; a.L = (int)L;
+  a.chan_first = g.chan_first; a.nchan_out = g.nchan_out;
+  cudaError_t e;
+  if (g.npol == 2) {
+    const size_t smem = low::ana_smem_bytes<2>();
+    e = cudaFuncSetAttribute(low::pfb_analysis_low<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    low::pfb_analysis_low<2><<<(unsigned)grid, 128, smem, st>>>(a);
+  } else {
+    const size_t smem = low::ana_smem_bytes<1>();
+    e = cudaFuncSetAttribute(low::pfb_analysis_low<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    low::pfb_analysis_low<1><<<(unsigned)grid, 64, smem, st>>>(a);
+  }
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return (int)e;
+  *k_lo = lo;
+  *k_hi = hi;
+  return 0;
+}
+
+// ---- inversion ---------------------------------------------------------------
 template <typename T>
 int low_inverse_plan_init(int nchan, int nu, int de, int Nf, int ov, int spans, int combine,
-                          const std::vector<T>& taper, const std::vector<double>& w, double gain,
-                          std::vector<void*>* allocs, const void** d_low, bool* enabled) {
+                          const std::vector<T>& taper, const void* d_wt, std::vector<void*>* allocs,
+                          const void** d_low, bool* enabled) {
   *enabled = false;
+  return 0;
+}
+
+template <>
+inline int low_inverse_plan_init<float>(int nchan, int nu, int de, int Nf, int ov, int spans, int combine,
+                                        const std::vector<float>& taper, const void* d_wt,
+                                        std::vector<void*>* allocs, const void** d_low, bool* enabled) {
+  *enabled = false;
+  if (!(Nf == 256 && nu == 4 && de == 3 && nchan % 16 == 0)) return 0;
+  low::LowInverse* h = new low::LowInverse();
+  int rc = low::upload_raw(taper, allocs, &h->taper);
+  std::vector<float2> t256 = low::unit_table(256, -1), t192 = low::unit_table(192, +1);
+  if (!rc) rc = low::upload_raw(t256, allocs, &h->tw256);
+  if (!rc) rc = low::upload_raw(t192, allocs, &h->tw192);
+  if (rc) { delete h; return rc; }
+  h->wt = reinterpret_cast<const low::C*>(d_wt);
+  h->nchan = nchan; h->keep = Nf - 2 * ov; h->ov2 = ov * de / nu; h->keep2 = 192 - 2 * h->ov2;
+  h->flip = spans ? 0 : 1;
+  h->chan_fast = (nchan == 256 && combine == 1) ? 1 : 0;
+  *d_low = h;
+  *enabled = true;
   return 0;
 }
 
@@ -32,9 +641,82 @@ int low_chan_idft_launch(const void* d_low, const void* in, void* out, int npol,
   return 0;
 }
 
+template <>
+inline int low_chan_idft_launch<float>(const void* d_low, const void* in, void* out, int npol, long long nrows,
+                                       cudaStream_t st, bool* done) {
+  *done = false;
+  const low::LowInverse* h = reinterpret_cast<const low::LowInverse*>(d_low);
+  if (!h->chan_fast) return 0;
+  low::ChanArgs a;
+  a.in = reinterpret_cast<const low::C*>(in);
+  a.out = reinterpret_cast<low::C*>(out);
+  a.tw256 = h->tw256;
+  a.nrows = nrows;
+  const size_t smem = (size_t)2 * 16 * low::kColStride * sizeof(low::C);
+  const int rows = 16 / npol;
+  long long npass = (nrows + rows - 1) / rows;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  long long grid = npass < (long long)sms * 3 ? npass : (long long)sms * 3;
+  cudaError_t e;
+  if (npol == 2) {
+    e = cudaFuncSetAttribute(low::pfb_chan_idft_low<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    low::pfb_chan_idft_low<2><<<(unsigned)grid, 256, smem, st>>>(a);
+  } else {
+    e = cudaFuncSetAttribute(low::pfb_chan_idft_low<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    low::pfb_chan_idft_low<1><<<(unsigned)grid, 256, smem, st>>>(a);
+  }
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return (int)e;
+  *done = true;
+  return 0;
+}
+
 template <typename T>
 int low_resample_launch(const void* d_low, const void* v, void* out, int npol, long long nblk, cudaStream_t st, bool* done) {
   *done = false;
+  return 0;
+}
+
+template <>
+inline int low_resample_launch<float>(const void* d_low, const void* v, void* out, int npol, long long nblk,
+                                      cudaStream_t st, bool* done) {
+  *done = false;
+  const low::LowInverse* h = reinterpret_cast<const low::LowInverse*>(d_low);
+  if (nblk > 2000000000ll) return 0;
+  low::ResArgs a;
+  a.v = reinterpret_cast<const low::C*>(v);
+  a.out = reinterpret_cast<low::C*>(out);
+  a.taper = h->taper; a.wt = h->wt; a.tw256 = h->tw256; a.tw192 = h->tw192;
+  a.nchan = h->nchan; a.keep = h->keep; a.ov2 = h->ov2; a.keep2 = h->keep2; a.flip = h->flip;
+  a.nblk = (int)nblk;
+  const int groups = h->nchan / (16 / npol);
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  long long nsplit = ((long long)sms * 2 + groups - 1) / groups;    // about one resident wave
+  if (nsplit > nblk) nsplit = nblk;
+  if (nsplit < 1) nsplit = 1;
+  a.nsplit = (int)nsplit;
+  const long long grid = nsplit * groups;
+  cudaError_t e;
+  if (npol == 2) {
+    const size_t smem = low::res_smem_bytes<2>();
+    e = cudaFuncSetAttribute(low::pfb_resample_low<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    low::pfb_resample_low<2><<<(unsigned)grid, 256, smem, st>>>(a);
+  } else {
+    const size_t smem = low::res_smem_bytes<1>();
+    e = cudaFuncSetAttribute(low::pfb_resample_low<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    low::pfb_resample_low<1><<<(unsigned)grid, 256, smem, st>>>(a);
+  }
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return (int)e;
+  *done = true;
   return 0;
 }
 

@@ -195,7 +195,10 @@ def test_segment_equals_oneshot(pst_taps):
     k_first, nblk = 29, 35
     s0 = k_first * 192 - 7
     seg = plan.segment(x[s0: s0 + 7 + nblk * 192 + 2880].contiguous(), s0, k_first, nblk)
-    assert torch.equal(seg, full[k_first:k_first + nblk])
+    # (the one-shot call runs the fast kernel, this short misaligned segment the generic one:
+    #  same blocks, same phase index, rounding-level differences only)
+    ref = full[k_first:k_first + nblk]
+    assert float((seg - ref).abs().max() / ref.abs().max()) < 2e-6
 
 
 def test_errors_are_loud():
