@@ -268,6 +268,8 @@ def run_b200(args):
     taps = load_pst_taps(normalise=True)
     shard = plan_time_shards(n_global, world, NCHAN, OS, 3072, NFFT, OVERLAP)[rank]
     rt = ShardedRoundTrip(shard, NCHAN, OS, taps, NFFT, OVERLAP, "tukey", True, NPOL, torch.complex64, dev)
+    if args.scratch_mib:
+        rt.inverse.set_scratch_bytes(args.scratch_mib << 20)
     rt.load_owned(synth_torch(shard.own0, shard.own_n, NPOL, dev))
     samples_rank = shard.own_n * NPOL
     osf = 4.0 / 3.0
@@ -349,23 +351,25 @@ def run_b200(args):
     pipeline = {"algorithmic_bytes_per_step": e2e_bytes, "gbs": e2e_bytes / (ms_step * 1e-3) / 1e9,
                 "frac": e2e_bytes / (ms_step * 1e-3) / 1e9 / peak, "ms_analysis": ms_analysis, "ms_inversion": ms_inverse}
 
-    # ---- e2e: pinned host buffers through the public operators ------------
+    # ---- e2e: pinned host buffers through the public streaming operator ------
+    # (H2D of the rank's samples incl. halo, kernels, D2H of the inverted series, overlapped
+    #  over time segments on three streams; the host buffer already holds every halo)
+    from ska_pst_dsp_model_b200.streaming import HostRoundTrip
     Ke = max(1, min(K, args.e2e_steps))
-    x_host = torch.empty((shard.own_n, NPOL), dtype=torch.complex64).pin_memory()
-    x_host.copy_(rt.local[: shard.own_n])
-    y_host = torch.empty((shard.out_n, NPOL), dtype=torch.complex64).pin_memory()
-
-    def e2e_step():
-        rt.local[: shard.own_n].copy_(x_host, non_blocking=True)
-        rt.step()
-        y_host.copy_(rt.out, non_blocking=True)
-
-    e2e_step()
+    x_host = torch.empty((shard.need_n, NPOL), dtype=torch.complex64).pin_memory()
+    x_host.copy_(rt.local[: shard.need_n])
+    del rt.chan
+    hrt = HostRoundTrip(shard.need_n, NCHAN, OS, taps, NFFT, OVERLAP, "tukey", True, NPOL, nseg=args.e2e_segments,
+                        device=dev, k_total=shard.fine_n)
+    assert hrt.n_out == shard.out_n
+    y_host = torch.empty((hrt.n_out, NPOL), dtype=torch.complex64).pin_memory()
+    hrt.run(x_host, y_host)
     barrier()
+    e2e_match = bool(torch.equal(y_host[:65536], rt.out[:65536].cpu()))
     s2, e2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s2.record()
     for _ in range(Ke):
-        e2e_step()
+        hrt.run(x_host, y_host)
     e2.record()
     barrier()
     ms_e2e = s2.elapsed_time(e2) / Ke
@@ -373,9 +377,12 @@ def run_b200(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_e2e = float(t.item())
+    h2d = sum(sg.need_n for sg in hrt.segs) * NPOL * cb
     e2e = {"value": total_samples / (ms_e2e * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": ms_e2e,
-           "h2d_bytes_per_step": shard.own_n * NPOL * cb, "d2h_bytes_per_step": shard.out_n * NPOL * cb,
-           "api": "sharding.ShardedRoundTrip.step() = ops.AnalysisPlan.segment + ops.InversePlan.__call__ over the C ABI"}
+           "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": hrt.n_out * NPOL * cb, "segments": len(hrt.segs),
+           "matches_device_resident_result": e2e_match,
+           "api": "streaming.HostRoundTrip.run(x_pinned, y_pinned): ops.AnalysisPlan.segment + ops.InversePlan over "
+                  "the C ABI, H2D/kernels/D2H overlapped per time segment"}
 
     # quick in-bench sanity check of the result against the input (not the oracle):
     # the round trip reproduces the delayed input (unity gain, deripple on)
@@ -431,6 +438,8 @@ def main():
     ap.add_argument("--log2-samples", type=int, default=24, help="samples per pol per GPU (default 2^24)")
     ap.add_argument("--cpu-log2-samples", type=int, default=22, help="bounded CPU sample per pol")
     ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--e2e-segments", type=int, default=16)
+    ap.add_argument("--scratch-mib", type=int, default=0, help="override the L2-resident inversion scratch size")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -541,6 +541,10 @@ static int inverse_run(pfb_inverse_plan* p, const void* in, void* out, int npol,
   const long long rowbytes = (long long)p->nchan * npol * sizeof(Cx<T>);
   long long B = (p->scratch_bytes - (long long)2 * p->ov * rowbytes) / ((long long)p->keep * rowbytes);
   if (B < 1) B = 1;
+  if (p->low_fast) {                    // equal work per CTA of the one-wave resample grid
+    const long long ns = low_resample_nsplit(p->d_low, npol);
+    if (B >= ns) B = B / ns * ns;
+  }
   if (B > nblocks) B = nblocks;
   const size_t need = (size_t)(((B - 1) * p->keep + p->Nf) * rowbytes);
   if (need > p->scratch_cap) {

@@ -675,6 +675,17 @@ inline int low_chan_idft_launch<float>(const void* d_low, const void* in, void* 
   return 0;
 }
 
+// preferred divisor of the chunk length (blocks) so every CTA of the resample wave gets equal work
+inline long long low_resample_nsplit(const void* d_low, int npol) {
+  const low::LowInverse* h = reinterpret_cast<const low::LowInverse*>(d_low);
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int groups = h->nchan / (16 / npol);
+  long long n = ((long long)sms * 2) / groups;
+  return n < 1 ? 1 : n;
+}
+
 template <typename T>
 int low_resample_launch(const void* d_low, const void* v, void* out, int npol, long long nblk, cudaStream_t st, bool* done) {
   *done = false;
@@ -697,7 +708,7 @@ inline int low_resample_launch<float>(const void* d_low, const void* v, void* ou
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  long long nsplit = ((long long)sms * 2 + groups - 1) / groups;    // about one resident wave
+  long long nsplit = ((long long)sms * 2) / groups;    // at most one resident wave (2 CTAs per SM)
   if (nsplit > nblk) nsplit = nblk;
   if (nsplit < 1) nsplit = 1;
   a.nsplit = (int)nsplit;

@@ -35,3 +35,74 @@ def read_fir_filter_coeff(file_path: str) -> np.ndarray:
     if ext == ".npy":
         return np.load(file_path).astype(np.float64).ravel()
     return np.loadtxt(file_path, dtype=np.float64).ravel()
+
+
+# ---------------------------------------------------------------------------
+# Prototype-filter designers.  The .mat files named by the reference configs are
+# git-ignored upstream, so they are re-created here with scipy.signal.firls
+# following matlab/design_PFB_FIR_filter.m:24-48 and
+# matlab/design_PFB_FIR_filter_two_stage.m:42-78.
+# ---------------------------------------------------------------------------
+def design_pfb_fir_filter(n_chan, os_nu, os_de, n_taps_per_chan):
+    """firls, order n_chan*taps_per_chan, bands [0, 1/N, (2 OS - 1)/N, 1], weights [1, 15]."""
+    from scipy.signal import firls
+    os_f = os_nu / os_de
+    if os_f == 1:
+        os_f += 0.1
+    fp, fs = 1.0 / n_chan, (2 * os_f - 1) / n_chan
+    return firls(n_chan * n_taps_per_chan + 1, [0, fp, fs, 1.0], [1, 1, 0, 0], weight=[1, 15])
+
+
+def design_pfb_fir_filter_two_stage(n_chan, os_nu, os_de, os_taps_per_chan=28, zero_stuff_factor=32):
+    """Stage-1 firls design at ``zero_stuff_factor`` x the band edges (0.998 Fs), then
+    FFT-domain zero stuffing (interpolation) to the full length (100 353 taps for Mid)."""
+    from scipy.signal import firls
+    os_f = os_nu / os_de
+    n_taps = int(round(os_taps_per_chan * n_chan / os_f))
+    n1 = n_taps // zero_stuff_factor
+    fp, fs = 1.0 / n_chan, (2 * os_f - 1) / n_chan
+    h0 = firls(n1 + 1, [0, fp * zero_stuff_factor, 0.998 * fs * zero_stuff_factor, 1.0], [1, 1, 0, 0], weight=[1, 15])
+    h1 = np.fft.fft(np.fft.ifftshift(h0))
+    hz = np.concatenate([h1[: n1 // 2 + 1], np.zeros(n1 * (zero_stuff_factor - 1)), h1[n1 // 2 + 1:]])
+    return np.real(np.fft.fftshift(np.fft.ifft(hz)))
+
+
+_DESIGN_CACHE = {}
+
+
+def resolve_fir_filter(path, config=None, config_dir=None):
+    """Coefficients for a config entry: an existing file wins; the shipped PST taps are
+    recognised by name; git-ignored upstream designs are re-created (and cached)."""
+    candidates = [path]
+    if config_dir is not None and not os.path.isabs(path):
+        candidates.append(os.path.join(config_dir, path))
+    for c in candidates:
+        if os.path.exists(c):
+            return read_fir_filter_coeff(c)
+    base = os.path.basename(path)
+    if base == "PST_filtertaps.txt":
+        return load_pst_taps()
+    design = (config or {}).get("fir_filter_design")
+    if design is None:
+        raise FileNotFoundError(f"FIR coefficient file {path} not found and no 'fir_filter_design' to re-create it")
+    nu, de = (int(v) for v in str(config["os_factor"]).split("/"))
+    key = (design, config["channels"], nu, de, config["fir_filter_taps"])
+    if key not in _DESIGN_CACHE:
+        cache = os.path.join(_DATA, "designed", f"{design}.{nu}-{de}.{config['channels']}.{config['fir_filter_taps']}.npy")
+        if os.path.exists(cache):
+            _DESIGN_CACHE[key] = np.load(cache)
+        else:
+            if design == "single_stage":
+                h = design_pfb_fir_filter(config["channels"], nu, de, (config["fir_filter_taps"] - 1) // config["channels"]
+                                          if config["fir_filter_taps"] % config["channels"] else config["fir_filter_taps"] // config["channels"])
+            elif design == "two_stage":
+                h = design_pfb_fir_filter_two_stage(config["channels"], nu, de)
+            else:
+                raise ValueError(f"unknown fir_filter_design {design!r}")
+            try:
+                os.makedirs(os.path.dirname(cache), exist_ok=True)
+                np.save(cache, h)
+            except OSError:
+                pass
+            _DESIGN_CACHE[key] = h
+    return _DESIGN_CACHE[key]

@@ -1,0 +1,170 @@
+"""DADA file object with the surface the reference uses from ``psr_formats.DADAFile``
+(test_backends.py:99-103, purity.py:277-279, pipeline.py:66-78) and the byte layout
+of the Matlab writers/readers:
+
+* header: ASCII ``KEY value`` lines, ``HDR_SIZE`` first (write_header.m:12-21), NUL
+  padded to HDR_SIZE (:33-43), size doubled until the text fits (:22-26); the reader
+  re-reads when HDR_SIZE != 4096 (read_header.m:29-36) and skips ``#`` lines (:20-22);
+* payload from byte HDR_SIZE: TFP order, polarisation fastest, then channel, then
+  time, interleaved (re, im) (write_dada_data.m:32-50, reshape_dada_data.m:21-27);
+  NBIT 32 -> float32, 64 -> float64 (write_dada_header.m:15-22); NDIM 2 = complex.
+
+``.data`` is a numpy array of shape ``(ndat, nchan, npol)``.
+"""
+from __future__ import annotations
+
+import os
+from collections import OrderedDict
+
+import numpy as np
+
+DEFAULT_HEADER = OrderedDict([
+    ("HDR_SIZE", "4096"), ("BW", "40"), ("DEC", "-45:59:09.5"), ("DSB", "0"), ("FREQ", "1405.000000"),
+    ("HDR_VERSION", "1.0"), ("INSTRUMENT", "dspsr"), ("MODE", "PSR"), ("NBIT", "32"), ("NCHAN", "1"),
+    ("NDIM", "2"), ("NPOL", "2"), ("OBS_OFFSET", "0"), ("PRIMARY", "dspsr"), ("RA", "16:44:49.28"),
+    ("SOURCE", "J1644-4559"), ("TELESCOPE", "PKS"), ("TSAMP", "0.025"), ("UTC_START", "2019-02-05-01:15:49"),
+])
+
+
+def parse_header(raw: bytes) -> "OrderedDict[str, str]":
+    text = raw.split(b"\0", 1)[0].decode("ascii", errors="replace")
+    hdr = OrderedDict()
+    for line in text.split("\n"):
+        line = line.strip()
+        if not line or line.startswith("#"):
+            continue
+        parts = line.split(None, 1)
+        if len(parts) == 2:
+            hdr[parts[0]] = parts[1].strip()
+    return hdr
+
+
+def read_header(path: str) -> "OrderedDict[str, str]":
+    size = 4096
+    with open(path, "rb") as f:
+        while True:
+            f.seek(0)
+            hdr = parse_header(f.read(size))
+            if "HDR_SIZE" in hdr:
+                new = int(hdr["HDR_SIZE"])
+                if new == size:
+                    return hdr
+                size = new
+            else:
+                size *= 2
+                if size > (1 << 28):
+                    raise ValueError(f"{path}: no HDR_SIZE key found")
+
+
+def format_header(header) -> bytes:
+    """Header bytes, growing HDR_SIZE by doubling until the text fits."""
+    header = OrderedDict((str(k), str(v)) for k, v in header.items())
+    size = int(header.get("HDR_SIZE", "4096"))
+    while True:
+        header["HDR_SIZE"] = str(size)
+        lines = [f"HDR_SIZE {size}"] + [f"{k} {header[k]}" for k in sorted(header) if k != "HDR_SIZE"]
+        text = ("\n".join(lines) + "\n").encode("ascii")
+        if len(text) <= size:
+            return text + b"\0" * (size - len(text))
+        size *= 2
+
+
+class DADAFile:
+    def __init__(self, file_path: str, header=None, data=None):
+        self.file_path = file_path
+        self._header = OrderedDict(header) if header is not None else OrderedDict(DEFAULT_HEADER)
+        self._data = None
+        if data is not None:
+            self.data = data
+        elif header is None and os.path.exists(file_path) and os.path.getsize(file_path) >= 4096:
+            self._header = read_header(file_path)
+
+    # -- header access -----------------------------------------------------
+    @property
+    def header(self):
+        return self._header
+
+    @header.setter
+    def header(self, h):
+        self._header = OrderedDict((str(k), str(v)) for k, v in h.items())
+
+    def __getitem__(self, key):
+        return self._header[key]
+
+    def __setitem__(self, key, value):
+        self._header[str(key)] = str(value)
+
+    def __contains__(self, key):
+        return key in self._header
+
+    @property
+    def nchan(self):
+        return int(self._header["NCHAN"])
+
+    @property
+    def npol(self):
+        return int(self._header["NPOL"])
+
+    @property
+    def ndim(self):
+        return int(self._header["NDIM"])
+
+    @property
+    def nbit(self):
+        return int(self._header["NBIT"])
+
+    @property
+    def ndat(self):
+        return 0 if self._data is None else self._data.shape[0]
+
+    # -- payload -------------------------------------------------------------
+    @property
+    def data(self):
+        return self._data
+
+    @data.setter
+    def data(self, arr):
+        arr = np.asarray(arr)
+        if arr.ndim == 1:
+            arr = arr[:, None, None]
+        if arr.ndim != 3:
+            raise ValueError("data must have shape (ndat, nchan, npol)")
+        self._data = arr
+        real_bits = arr.real.dtype.itemsize * 8
+        self._header["NBIT"] = str(real_bits)
+        self._header["NDIM"] = "2" if np.iscomplexobj(arr) else "1"
+        self._header["NCHAN"] = str(arr.shape[1])
+        self._header["NPOL"] = str(arr.shape[2])
+
+    def _dtype(self):
+        real = {32: np.float32, 64: np.float64, 16: np.int16, 8: np.int8}[self.nbit]
+        return real
+
+    def load_data(self):
+        self._header = read_header(self.file_path)
+        hdr_size = int(self._header["HDR_SIZE"])
+        real = self._dtype()
+        raw = np.fromfile(self.file_path, dtype=real, offset=hdr_size)
+        if self.ndim == 2:
+            raw = raw[: raw.size // 2 * 2]
+            if real in (np.float32, np.float64):
+                raw = raw.view(np.complex64 if real is np.float32 else np.complex128)
+            else:
+                raw = raw[0::2].astype(np.float32) + 1j * raw[1::2].astype(np.float32)
+        per = self.nchan * self.npol
+        ndat = raw.size // per
+        self._data = raw[: ndat * per].reshape(ndat, self.nchan, self.npol)
+        return self
+
+    def dump_data(self, overwrite=True):
+        if self._data is None:
+            raise RuntimeError("no data to dump")
+        if os.path.exists(self.file_path) and not overwrite:
+            raise FileExistsError(self.file_path)
+        d = os.path.dirname(os.path.abspath(self.file_path))
+        os.makedirs(d, exist_ok=True)
+        with open(self.file_path, "wb") as f:
+            f.write(format_header(self._header))
+            np.ascontiguousarray(self._data).tofile(f)
+        self._header = parse_header(format_header(self._header))
+        return self

@@ -44,14 +44,15 @@ class TimeShard:
     out_n: int
 
 
-def plan_time_shards(n_dat, world, nchan, os_factor, ntaps, input_fft_length, input_overlap):
+def plan_time_shards(n_dat, world, nchan, os_factor, ntaps, input_fft_length, input_overlap, k_total=None):
     """Cut a stream of ``n_dat`` samples/pol into ``world`` time shards for the
     Bunton analysis + inversion round trip."""
     osf = Rational.from_str(os_factor)
     step = nchan * osf.de // osf.nu
     fl = -(-ntaps // nchan) * nchan
     keep = input_fft_length - 2 * input_overlap
-    k_total = max((n_dat - fl) // step, 0)
+    if k_total is None:
+        k_total = max((n_dat - fl) // step, 0)      # polyphase_analysis.m:62
     nb_total = max((k_total - 2 * input_overlap) // keep, 0) if k_total >= 2 * input_overlap else 0
     if nb_total < world:
         raise ValueError(f"stream too short: {nb_total} overlap-save blocks for {world} shards")

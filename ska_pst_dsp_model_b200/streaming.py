@@ -1,0 +1,81 @@
+"""Host-resident streams: analysis + inversion with the H2D copy, the kernels and
+the D2H copy of successive time segments overlapped on three CUDA streams.
+
+This is the executor behind the end-to-end number (`e2e` in bench.py) and the
+file-level operators for large inputs: the reference moves data between stages
+only as files / host arrays (python/data_gen/pipeline.py:62-84), so a drop-in
+backend is fed from host memory and PCIe is the bound; segments are cut like the
+multi-GPU time shards (sharding.plan_time_shards) and need no exchange because the
+host buffer already holds every halo.
+"""
+from __future__ import annotations
+
+from .sharding import plan_time_shards
+
+
+class HostRoundTrip:
+    def __init__(self, n_dat, nchan, os_factor, taps, input_fft_length, input_overlap, temporal_taper="tukey",
+                 deripple=True, npol=2, nseg=16, dtype=None, device=None, k_total=None):
+        import torch
+        from . import ops
+        self.torch = torch
+        dtype = dtype or torch.complex64
+        self.npol = npol
+        self.analysis = ops.AnalysisPlan(nchan, os_factor, taps, "polyphase_analysis", dtype=dtype, device=device)
+        self.inverse = ops.InversePlan(nchan, os_factor, input_fft_length, input_overlap, temporal_taper,
+                                       deripple_taps=taps if deripple else None, dtype=dtype, device=device)
+        dev = self.analysis.device
+        self.device = dev
+        nseg = max(1, nseg)
+        while True:
+            try:
+                self.segs = plan_time_shards(n_dat, nseg, nchan, os_factor, len(taps), input_fft_length,
+                                             input_overlap, k_total=k_total)
+                break
+            except ValueError:
+                if nseg == 1:
+                    raise
+                nseg //= 2
+        self.n_out = self.segs[-1].out0 + self.segs[-1].out_n
+        mx_in = max(s.need_n for s in self.segs)
+        mx_fine = max(s.fine_n for s in self.segs)
+        mx_out = max(s.out_n for s in self.segs)
+        self.din = [torch.empty((mx_in, npol), dtype=dtype, device=dev) for _ in range(2)]
+        self.dchan = [torch.empty((mx_fine, nchan, npol), dtype=dtype, device=dev) for _ in range(2)]
+        self.dout = [torch.empty((mx_out, npol), dtype=dtype, device=dev) for _ in range(2)]
+        self.s_in, self.s_cmp, self.s_out = (torch.cuda.Stream(dev) for _ in range(3))
+
+    def run(self, x_host, y_host):
+        """x_host: pinned [n_dat, npol]; y_host: pinned [n_out, npol]. Returns after the work is
+        enqueued; the caller's current stream waits for the last D2H copy."""
+        torch = self.torch
+        cur = torch.cuda.current_stream(self.device)
+        for s in (self.s_in, self.s_cmp, self.s_out):
+            s.wait_stream(cur)
+        ev_cmp = [None, None]     # compute finished reading din[slot] / writing dout[slot]
+        ev_out = [None, None]     # D2H finished reading dout[slot]
+        for g, sg in enumerate(self.segs):
+            slot = g & 1
+            with torch.cuda.stream(self.s_in):
+                if ev_cmp[slot] is not None:
+                    self.s_in.wait_event(ev_cmp[slot])
+                self.din[slot][: sg.need_n].copy_(x_host[sg.need0: sg.need0 + sg.need_n], non_blocking=True)
+                ev_in = torch.cuda.Event()
+                ev_in.record(self.s_in)
+            with torch.cuda.stream(self.s_cmp):
+                self.s_cmp.wait_event(ev_in)
+                if ev_out[slot] is not None:
+                    self.s_cmp.wait_event(ev_out[slot])
+                ch = self.dchan[slot][: sg.fine_n]
+                self.analysis.segment(self.din[slot][: sg.need_n], sg.need0, sg.fine0, sg.fine_n, out=ch)
+                self.inverse(ch, out=self.dout[slot][: sg.out_n])
+                ev_cmp[slot] = torch.cuda.Event()
+                ev_cmp[slot].record(self.s_cmp)
+            with torch.cuda.stream(self.s_out):
+                self.s_out.wait_event(ev_cmp[slot])
+                y_host[sg.out0: sg.out0 + sg.out_n].copy_(self.dout[slot][: sg.out_n], non_blocking=True)
+                ev_out[slot] = torch.cuda.Event()
+                ev_out[slot].record(self.s_out)
+        cur.wait_stream(self.s_out)
+        cur.wait_stream(self.s_cmp)
+        return y_host

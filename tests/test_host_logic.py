@@ -1,0 +1,163 @@
+"""CPU tests of the host-side mirror of the reference interface (no GPU, no compute)."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle import pfb_oracle as o
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_capi_exports_every_declared_symbol():
+    """The shared library loads and exports exactly what include/pfb_b200.h declares."""
+    from ska_pst_dsp_model_b200 import lib
+    hdr = open(os.path.join(ROOT, "include", "pfb_b200.h")).read()
+    declared = set(re.findall(r"\b(pfb_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    for name in sorted(declared):
+        assert hasattr(lib.lib, name), f"{name} declared in pfb_b200.h but not exported"
+    assert declared == set(lib.EXPORTS)
+    assert lib.lib.pfb_version() >= 100
+
+
+def test_plan_argument_errors_need_no_gpu_compute():
+    import ctypes
+    from ska_pst_dsp_model_b200 import lib
+    h = ctypes.c_void_p()
+    taps = (ctypes.c_double * 4)(1, 2, 3, 4)
+    rc = lib.lib.pfb_analysis_plan_create(ctypes.byref(h), 0, 8, 7, 8, taps, 4, 0, 0)     # os_de > os_nu
+    assert rc == -1 and b"bad argument" in lib.lib.pfb_last_error()
+    rc = lib.lib.pfb_analysis_plan_create(ctypes.byref(h), 0, 8, 8, 7, taps, 4, 5, 0)     # bad dtype
+    assert rc == -1
+    rc = lib.lib.pfb_inverse_plan_create(ctypes.byref(h), 8, 8, 7, 60, 8, None, None, 0, 1, 1, 0, 0)
+    assert rc == -1 and b"divisible" in lib.lib.pfb_last_error()
+
+
+def test_rational():
+    from ska_pst_dsp_model_b200.rational import Rational
+    r = Rational.from_str("8/7")
+    assert r.normalize(32) == 28 and r.multiply(28) == 32 and str(r) == "8/7"
+    assert Rational.from_str("4/3") == "4/3" and float(Rational(32, 27)) == 32 / 27
+    assert Rational.from_str(r) is r
+    # test_dspsr_util.py:77-81 pins output_fft_length = 8 ch * 32768 * 7/8
+    assert r.normalize(32768) * 8 == 229376
+
+
+def test_windows_match_oracle():
+    from ska_pst_dsp_model_b200 import fft_windows as w
+    assert np.array_equal(w.tukey_window(256, 48), o.window_tukey(256, 48))
+    assert np.array_equal(w.top_hat_window(64, 8), o.window_top_hat(64, 8))
+    assert np.array_equal(w.no_window(16), np.ones(16))
+    assert np.allclose(w.hann_window(33), o.hann(33))
+    with pytest.raises(KeyError):
+        w.make_window("blackman", 8, 1)
+
+
+def test_partialize_semantics():
+    from ska_pst_dsp_model_b200.partialize import partialize
+
+    @partialize
+    def f(a, b=1, backend="x"):
+        return (a, b, backend)
+
+    g = f(backend="python")
+    assert callable(g) and g(3) == (3, 1, "python") and g(3, b=2) == (3, 2, "python")
+    assert f(5) == (5, 1, "x")
+
+
+def test_dada_header_roundtrip_and_growth(tmp_path):
+    from ska_pst_dsp_model_b200.formats import DADAFile, format_header, parse_header
+    rng = np.random.default_rng(0)
+    d = (rng.standard_normal((100, 4, 2)) + 1j * rng.standard_normal((100, 4, 2))).astype(np.complex64)
+    f = DADAFile(str(tmp_path / "a.dump"))
+    f.data = d
+    f["OS_FACTOR"] = "8/7"
+    f.dump_data()
+    g = DADAFile(f.file_path).load_data()
+    assert g["HDR_SIZE"] == "4096" and g["NCHAN"] == "4" and g["NPOL"] == "2" and g["NBIT"] == "32"      # test_read_dada_file.m:11-24
+    assert np.array_equal(g.data, d) and g.nchan == 4 and g.npol == 2
+    raw = open(f.file_path, "rb").read()
+    assert raw.startswith(b"HDR_SIZE 4096\n") and raw[4095:4096] == b"\0" and len(raw) == 4096 + d.nbytes
+    # payload order: pol fastest, then channel, then time, (re, im) interleaved
+    pay = np.frombuffer(raw[4096:], dtype=np.float32)
+    assert pay[0] == d[0, 0, 0].real and pay[1] == d[0, 0, 0].imag and pay[2] == d[0, 0, 1].real and pay[4] == d[0, 1, 0].real
+    # header growth by doubling (write_header.m:22-26; test_write_dada_file.m:51,57 expects 8192)
+    g["COEFF_0"] = ",".join("%0.6E" % c for c in np.arange(400))
+    g.file_path = str(tmp_path / "b.dump")
+    g.dump_data()
+    h = DADAFile(g.file_path).load_data()
+    assert h["HDR_SIZE"] == "8192" and np.array_equal(h.data, d) and len(h["COEFF_0"].split(",")) == 400
+    # comments are skipped (read_header.m:20-22)
+    assert "X" not in parse_header(b"HDR_SIZE 4096\n# X 1\nA b\n\0\0")
+    f64 = DADAFile(str(tmp_path / "c.dump"))
+    f64.data = d.astype(np.complex128)
+    assert f64["NBIT"] == "64"
+    f64.dump_data()
+    assert np.array_equal(DADAFile(f64.file_path).load_data().data, d.astype(np.complex128))
+
+
+def test_generate_test_vector_naming_and_content(tmp_path):
+    from ska_pst_dsp_model_b200 import data_gen
+    gen = data_gen.generate_test_vector(backend="python", n_bins=1000)
+    f = gen([0.1], [1], domain_name="time", output_dir=str(tmp_path), n_pol=2)
+    # python/test/test_data_gen.py:89-93
+    assert os.path.basename(f.file_path) == "time_domain_impulse.1000.0.100-1.000.2.single.python.dump"
+    assert f.data.shape == (1000, 1, 2) and f.data[100, 0, 0] == 1 and f.data.sum() == 2
+    s = data_gen.generate_test_vector([0.01], [np.pi / 4], 0.0, n_bins=500, domain_name="freq", backend="python",
+                                      output_dir=str(tmp_path))
+    assert np.allclose(s.data[:, 0, 0], o.complex_sinusoid(500, [0.01], [np.pi / 4], 0.0))
+    assert np.array_equal(data_gen.time_domain_impulse(50, [7], [2]), o.time_domain_impulse(50, [7], [2]))
+
+
+def test_config_and_filter_resolution():
+    from ska_pst_dsp_model_b200.data_gen.config import load_config
+    from ska_pst_dsp_model_b200.filters import load_pst_taps, resolve_fir_filter
+    low = load_config("low")
+    assert low["channels"] == 256 and low["os_factor"] == "4/3" and low["input_overlap"] == 48
+    mid = load_config("mid")
+    assert mid["analysis_function"] == "polyphase_analysis_padded" and mid["fir_filter_taps"] == 100353
+    t = load_pst_taps()
+    # shipped taps invariants: 3072 integer taps, sum 16 777 241, peak at 1536, symmetric about it
+    assert t.size == 3072 and t.sum() == 16777241 and t.argmax() == 1536 and np.array_equal(t[1:], t[1:][::-1])
+    assert np.array_equal(resolve_fir_filter("whatever/PST_filtertaps.txt"), t)
+    with pytest.raises(FileNotFoundError):
+        resolve_fir_filter("missing.mat")
+
+
+def test_designed_filters_match_oracle_designs():
+    from ska_pst_dsp_model_b200.filters import design_pfb_fir_filter
+    h = design_pfb_fir_filter(256, 4, 3, 12)
+    ho = o.design_pfb_fir_filter(256, "4/3", 12)
+    assert h.size == 3073 and np.allclose(h, ho) and np.allclose(h, h[::-1]) and abs(h.sum() - 1) < 1e-3
+
+
+def test_time_shard_plan_covers_stream():
+    from ska_pst_dsp_model_b200.sharding import plan_time_shards
+    n = 1 << 22
+    for world in (1, 2, 3, 8):
+        sh = plan_time_shards(n, world, 256, "4/3", 3072, 256, 48)
+        k_total = (n - 3072) // 192
+        nb_total = (k_total - 96) // 160
+        assert sum(s.inv_nblocks for s in sh) == nb_total
+        assert sh[0].own0 == 0 and sh[-1].own0 + sh[-1].own_n == n
+        for a, b in zip(sh[:-1], sh[1:]):
+            assert a.own0 + a.own_n == b.own0 and a.out0 + a.out_n == b.out0
+            assert a.halo_n == 96 * 192 + 3072 - 192 and b.send_n == a.halo_n      # 2*ov*S + fl - S
+            assert a.fine0 % 4 == 0 and b.own0 % 256 == 0                           # phase index restarts cleanly
+        assert all(s.need0 + s.need_n <= n for s in sh)
+    with pytest.raises(ValueError):
+        plan_time_shards(3072 + 192 * 300, 8, 256, "4/3", 3072, 256, 48)
+
+
+def test_purity_driver_parameters():
+    """purity.py:79-99 bookkeeping (no compute)."""
+    from ska_pst_dsp_model_b200.verify.purity import TestPurity
+    t = TestPurity(n_test=5, os_factor="4/3", input_fft_length=256, input_overlap=48, fft_window="tukey",
+                   deripple=True, channels=256, fir_filter_taps=3072, fir_filter_coeff_file_path="PST_filtertaps.txt",
+                   blocks=3)
+    assert t.block_size == 49152 and t.n_samples == 147456 and t.fft_size == 98304
+    assert t.total_sample_shift == 36 * 256 + 1535
+    assert list(t.time_domain_args["offset"]) == list(np.linspace(1, 147456, 5).astype(int))
+    assert list(t.freq_domain_args["frequency"]) == list(np.linspace(1, 49152, 5).astype(int) * 3)
