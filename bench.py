@@ -166,56 +166,62 @@ def run_reference(args):
 
 # --------------------------------------------------------------------------
 class ClockSampler:
-    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock / throttle reasons sampled through NVML from a thread every ~1 ms
+    (nvidia-smi -lms cannot resolve a timed region of a few milliseconds)."""
 
     def __init__(self, index):
         self.index = index
-        self.lines = []
-        self.proc = None
+        self.samples = []
+        self.stop_flag = False
+        self.thread = None
+        self.h = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100",
-                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.smax = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.thread = threading.Thread(target=self._poll, daemon=True)
             self.thread.start()
-        except Exception:
-            self.proc = None
+        except Exception as e:          # noqa: BLE001
+            self.h = None
+            self.err = repr(e)
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append((time.perf_counter(), line.strip()))
+    def _poll(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                clk = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                self.samples.append((time.perf_counter(), clk, rs, pw))
+            except Exception:           # noqa: BLE001
+                pass
+            time.sleep(0.001)
 
     def stop(self, t_begin, t_end):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, smax, reasons, power = [], None, set(), []
-        for ts, line in self.lines:
-            parts = [p.strip() for p in line.split(",")]
-            if len(parts) < 9:
-                continue
-            try:
-                clk, mx = float(parts[1]), float(parts[2])
-            except ValueError:
-                continue
-            smax = mx
-            if t_begin - 0.05 <= ts <= t_end + 0.05:
-                sm.append(clk)
-                try:
-                    power.append(float(parts[3]))
-                except ValueError:
-                    pass
-                names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-                for nm, val in zip(names, parts[5:9]):
-                    if val.lower().startswith("active"):
-                        reasons.add(nm)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": smax,
-                "reasons": sorted(reasons), "samples": len(sm), "power_w_max": max(power) if power else None}
+        if self.h is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable: " + getattr(self, "err", "?")]}
+        self.stop_flag = True
+        self.thread.join(timeout=1.0)
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        inside = [s for s in self.samples if t_begin <= s[0] <= t_end] or self.samples[-3:]
+        reasons = set()
+        for _, _, rs, _ in inside:
+            for nm, bit in names.items():
+                if rs & bit:
+                    reasons.add(nm)
+        clks = [s[1] for s in inside]
+        return {"sm_mhz": statistics.median(clks) if clks else None, "sm_max_mhz": self.smax,
+                "reasons": sorted(reasons), "samples": len(inside),
+                "power_w_max": max(s[3] for s in inside) if inside else None}
 
 
 def load_peak():
@@ -290,7 +296,7 @@ def run_b200(args):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-        time.sleep(0.25)
+        time.sleep(0.05)
     launches0 = ops.launch_count()
     barrier()
     t_begin = time.perf_counter()

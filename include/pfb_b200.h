@@ -84,7 +84,7 @@ long long pfb_inverse_out_len(const pfb_inverse_plan* plan, long long n_dat); /*
 /* in: [n_dat][nchan][npol]; out: [out_len][npol] */
 int pfb_inverse_execute(pfb_inverse_plan* plan, const void* in_dev, void* out_dev, int npol,
                         long long n_dat, void* stream);
-/* bytes of L2-resident scratch used between the two inversion kernels (default 32 MiB) */
+/* bytes of scratch between the two inversion kernels (default 128 MiB; <= ~64 MiB keeps it L2-resident) */
 int pfb_inverse_set_scratch_bytes(pfb_inverse_plan* plan, long long bytes);
 /* run only one stage of the chain over the whole input (profiling / roofline):
  * stage 0 = channel IDFT into the caller's v buffer [n_dat][nchan][npol],

@@ -158,7 +158,7 @@ struct pfb_inverse_plan {
   const void* d_wt = nullptr;
   const void* d_low = nullptr;       // fast-path tables (pfb_low.cuh)
   bool low_fast = false;
-  long long scratch_bytes = 32ll << 20;
+  long long scratch_bytes = 128ll << 20;
   void* d_scratch = nullptr;
   size_t scratch_cap = 0;
   DeviceTables tabs;

@@ -34,7 +34,7 @@ struct AnalysisArgs {
 
 template <typename T>
 __global__ void __launch_bounds__(256) pfb_analysis_generic(const AnalysisArgs a) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   Cx<T>* s = reinterpret_cast<Cx<T>*>(smem_raw);
   const int N = a.N, npol = a.npol, ld = padded_len<T>(N);
   const long long k0 = (long long)blockIdx.x * a.kb;
@@ -100,7 +100,7 @@ struct ChanIdftArgs {
 
 template <typename T>
 __global__ void __launch_bounds__(256) pfb_chan_idft_generic(const ChanIdftArgs a) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   Cx<T>* s = reinterpret_cast<Cx<T>*>(smem_raw);
   const int n = a.nchan, npol = a.npol, ld = padded_len<T>(n);
   const long long r0 = (long long)blockIdx.x * a.rb;
@@ -148,7 +148,7 @@ struct ResampleArgs {
 
 template <typename T>
 __global__ void __launch_bounds__(256) pfb_resample_generic(const ResampleArgs a) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   const int ncol = a.tg * a.npol;
   const int ldA = padded_len<T>(a.Nf), ldB = padded_len<T>(a.FNw);
   Cx<T>* sA = reinterpret_cast<Cx<T>*>(smem_raw);

@@ -290,7 +290,7 @@ constexpr int kQStride = 17;
 
 template <int NPOL>
 __global__ void __launch_bounds__(256, 3) pfb_chan_idft_low(const ChanArgs a) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   C* ex = reinterpret_cast<C*>(smem_raw);    // [2][16 ffts][273]
   const int tid = threadIdx.x;
   // lanes: (q, pol) contiguous in memory; 16 FFTs per CTA pass = 16/NPOL rows
@@ -358,7 +358,7 @@ template <int NPOL> constexpr size_t res_smem_bytes() {
 
 template <int NPOL>
 __global__ void __launch_bounds__(256, 2) pfb_resample_low(const ResArgs a) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   C* exA = reinterpret_cast<C*>(smem_raw);            // [16 cols][273]  phase 1 -> 2
   C* exB = exA + 16 * kColStride;                     // [16 cols][273]  phase 2 -> 3 ([m][o] stride 17)
   C* swt = exB + 16 * kColStride;                     // [16 cols][193]  weights of this column group
