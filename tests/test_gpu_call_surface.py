@@ -1,0 +1,105 @@
+"""GPU tests through the reference's Python call surface (files in, files out)."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import pfb_oracle as o
+
+pytestmark = pytest.mark.gpu
+
+
+def nerr(a, b):
+    return float(np.abs(a - b).max() / np.abs(b).max())
+
+
+def test_channelize_synthesize_files_low(tmp_path, pst_taps):
+    from ska_pst_dsp_model_b200 import data_gen
+    from ska_pst_dsp_model_b200.formats import DADAFile
+    data_gen.set_config("low_pst")
+    d = str(tmp_path)
+    n = 256 * 192 * 3
+    gen = data_gen.generate_test_vector(backend="python", n_bins=n, n_pol=2)
+    src = gen([30000], [1], domain_name="time", output_dir=d)
+    ch = data_gen.channelize(src.file_path, output_dir=d, backend="b200")
+    assert os.path.basename(ch.file_path) == "channelize.256.4-3.dump"            # channelize.py:58-62
+    assert ch.data.shape == ((n - 3072) // 192, 256, 2)
+    assert ch["OS_FACTOR"] == "4/3" and ch["NCHAN"] == "256" and ch["PFB_DC_CHAN"] == "1" and ch["NCHAN_PFB_0"] == "256"
+    assert ch["NTAP_0"] == "3072" and ch["NSTAGE"] == "1" and int(ch["HDR_SIZE"]) >= 65536
+    assert abs(float(ch["TSAMP"]) - 0.025 * 256 * 3 / 4) < 1e-12
+    h = pst_taps                      # raw integer taps, as the config file holds them
+    xo = np.transpose(src.data, (2, 1, 0)).astype(np.complex128)
+    ref = o.polyphase_analysis(xo, h, 256, "4/3")
+    assert nerr(np.transpose(ch.data, (2, 1, 0)), ref) < 1e-5
+    inv = data_gen.synthesize(ch.file_path, fft_window_str="tukey", deripple=True, backend="b200", output_dir=d)
+    assert os.path.basename(inv.file_path) == "synthesize.256.dump"                 # synthesize.py:60-63
+    # the synthesizer takes its deripple taps from COEFF_0 (%0.6E, add_fir_filter_to_header.m:14)
+    coeff = np.array([float(v) for v in ch["COEFF_0"].split(",")])
+    ref_inv = o.polyphase_synthesis(np.transpose(ch.data, (2, 1, 0)).astype(np.complex128), True, 256, "4/3", coeff, 1, 48,
+                                    o.window_tukey(256, 48))
+    got = np.transpose(DADAFile(inv.file_path).load_data().data, (2, 1, 0))
+    assert got.shape == ref_inv.shape and nerr(got, ref_inv) < 1e-5
+    assert abs(float(inv["TSAMP"]) - 0.025) < 1e-12
+
+
+def test_channelize_cfg1_matches_oracle(tmp_path, pst_taps):
+    """BASELINE configs[0]: 8 channels, OS 8/7, PST taps, 2^18 complex64 single-pol impulse."""
+    from ska_pst_dsp_model_b200 import data_gen
+    data_gen.set_config("test")
+    d = str(tmp_path)
+    n = 1 << 18
+    src = data_gen.generate_test_vector([0.11], [1], n_bins=n, domain_name="time", backend="python", output_dir=d)
+    ch = data_gen.channelize(backend="python")(src.file_path, channels=8, os_factor_str="8/7", output_dir=d)
+    assert ch.data.shape == (37010, 8, 1)
+    ref = o.polyphase_analysis(np.transpose(src.data, (2, 1, 0)).astype(np.complex128), pst_taps, 8, "8/7")
+    assert nerr(np.transpose(ch.data, (2, 1, 0)), ref) < 1e-5
+
+
+def test_backends_driver_with_oracle_backend(tmp_path, pst_taps):
+    """verify.test_backends: the b200 channelizer against a second backend (here the oracle,
+    registered from the test side) at the reference's atol = rtol = 1e-4."""
+    from ska_pst_dsp_model_b200 import data_gen
+    from ska_pst_dsp_model_b200.data_gen import channelize as chmod
+    from ska_pst_dsp_model_b200.filters import resolve_fir_filter
+    from ska_pst_dsp_model_b200.formats import DADAFile
+    from ska_pst_dsp_model_b200.verify.test_backends import TestBackends
+    data_gen.set_config("low_pst")
+
+    def oracle_backend(f, channels, os_str, fir_path, output_dir, output_file_name, use_padded):
+        taps = resolve_fir_filter(fir_path)
+        taps = taps / taps.sum()
+        fn = o.polyphase_analysis_padded if use_padded else o.polyphase_analysis
+        y = fn(np.transpose(f.data, (2, 1, 0)).astype(np.complex128), taps, channels, os_str)
+        out = DADAFile(os.path.join(output_dir, output_file_name), header=f.header)
+        out.data = np.transpose(y, (2, 1, 0)).astype(np.complex64)
+        return out.dump_data()
+
+    chmod.register_backend("oracle", oracle_backend)
+    norm = tmp_path / "taps.npy"
+    np.save(norm, pst_taps / pst_taps.sum())
+    t = TestBackends("4/3", 256, 256, str(norm), blocks=2, backends=("b200", "oracle"), output_dir=str(tmp_path))
+    res = t.test_channelizer_backends()
+    assert res["oracle"]["mean"] == 1.0
+
+
+def test_purity_driver_meets_requirement(tmp_path, pst_taps):
+    """verify.purity on a handful of vectors: -60 dB temporal and spectral purity (TestImpulse.m / TestPureTone.m)."""
+    from ska_pst_dsp_model_b200 import data_gen
+    from ska_pst_dsp_model_b200.verify.purity import TestPurity
+    data_gen.set_config("low_pst")
+    norm = tmp_path / "taps.npy"
+    np.save(norm, pst_taps / pst_taps.sum())
+    t = TestPurity(n_test=4, os_factor="4/3", input_fft_length=256, input_overlap=48, fft_window="tukey", deripple=True,
+                   channels=256, fir_filter_taps=3072, fir_filter_coeff_file_path=str(norm), blocks=3,
+                   output_dir=str(tmp_path))
+    # keep the offsets where an inverted impulse exists (the last offset lies beyond the inverted span)
+    t.time_domain_args["offset"] = np.array([12000, 40000, 70000])
+    t.temporal_purity()
+    t.spectral_purity()
+    worst = t.check(-60.0)
+    assert set(worst) == {"test_time_domain_impulse", "test_complex_sinusoid"}
+    path = t.finish()
+    import json
+    rep = json.load(open(path))
+    assert set(rep["test_time_domain_impulse"][0]) == {"mean_diff", "total_diff", "max_spurious_power",
+                                                        "total_spurious_power", "mean_spurious_power", "arg"}
