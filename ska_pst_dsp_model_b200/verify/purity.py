@@ -117,19 +117,19 @@ class TestPurity:
             return {"mean_diff": d["mean"], "total_diff": d["sum"], "max_spurious_power": t["max_spurious"],
                     "total_spurious_power": t["total_spurious"], "mean_spurious_power": t["mean_spurious"]}
 
-        self._test(test_vector_func=lambda o: func([o]), test_vector_args=self.time_domain_args["offset"],
+        self._test(test_vector_func=func, test_vector_args=self.time_domain_args["offset"],
                    test_method_name="test_time_domain_impulse", report_func=report)
 
     def spectral_purity(self):
         func = dg_util.rpartial(functools.partial(self.pipeline, domain_name="freq"),
-                                [self.freq_domain_args["phase"]], self.freq_domain_args["bin_offset"])
+                                self.freq_domain_args["phase"], self.freq_domain_args["bin_offset"])
 
         def report(time_prod, freq_prod):
             d, t = time_prod["diff"], freq_prod["this"][1]
             return {"mean_diff": d["mean"], "total_diff": d["sum"], "max_spurious_power": t["max_spurious"],
                     "total_spurious_power": t["total_spurious"], "mean_spurious_power": t["mean_spurious"]}
 
-        self._test(test_vector_func=lambda f: func([f]), test_vector_args=self.freq_domain_args["frequency"],
+        self._test(test_vector_func=func, test_vector_args=self.freq_domain_args["frequency"],
                    test_method_name="test_complex_sinusoid", report_func=report)
 
     def dispose(self):

@@ -59,7 +59,7 @@ def test_backends_driver_with_oracle_backend(tmp_path, pst_taps):
     """verify.test_backends: the b200 channelizer against a second backend (here the oracle,
     registered from the test side) at the reference's atol = rtol = 1e-4."""
     from ska_pst_dsp_model_b200 import data_gen
-    from ska_pst_dsp_model_b200.data_gen import channelize as chmod
+    from ska_pst_dsp_model_b200.data_gen.channelize import register_backend
     from ska_pst_dsp_model_b200.filters import resolve_fir_filter
     from ska_pst_dsp_model_b200.formats import DADAFile
     from ska_pst_dsp_model_b200.verify.test_backends import TestBackends
@@ -74,7 +74,7 @@ def test_backends_driver_with_oracle_backend(tmp_path, pst_taps):
         out.data = np.transpose(y, (2, 1, 0)).astype(np.complex64)
         return out.dump_data()
 
-    chmod.register_backend("oracle", oracle_backend)
+    register_backend("oracle", oracle_backend)
     norm = tmp_path / "taps.npy"
     np.save(norm, pst_taps / pst_taps.sum())
     t = TestBackends("4/3", 256, 256, str(norm), blocks=2, backends=("b200", "oracle"), output_dir=str(tmp_path))
