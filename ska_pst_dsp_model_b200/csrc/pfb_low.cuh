@@ -125,7 +125,9 @@ template <int NPOL> constexpr size_t ana_smem_bytes() {
   return (size_t)kAnaStages * kTileSamples * NPOL * sizeof(C) + (size_t)64 * NPOL * kExStride * sizeof(C) + 64;
 }
 
-template <int NPOL>
+// FULL: all 256 channels are written in natural order (Bunton); otherwise the runtime channel
+// window (chan_first, nchan_out) of the lowcbf variant applies.
+template <int NPOL, bool FULL>
 __global__ void __launch_bounds__(64 * NPOL, NPOL == 2 ? 2 : 4) pfb_analysis_low(const AnaArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   C* ring = reinterpret_cast<C*>(smem_raw);                                  // [stage][768][NPOL]
@@ -253,7 +255,7 @@ __global__ void __launch_bounds__(64 * NPOL, NPOL == 2 ? 2 : 4) pfb_analysis_low
         if (q & 1) asm volatile("" ::: "memory");   // keep at most two butterflies in flight (register budget)
       }
       const long long kb = kA + 16ll * it + tj;
-      C* op = a.out + ((a.kout0 + kb) * a.nchan_out) * NPOL + tp;
+      C* op = a.out + ((a.kout0 + kb) * (FULL ? 256 : a.nchan_out)) * NPOL + tp + (FULL ? o * NPOL : 0);
       const bool live = kb < kend;
 #pragma unroll
       for (int o1 = 0; o1 < 8; ++o1) {
@@ -263,9 +265,13 @@ __global__ void __launch_bounds__(64 * NPOL, NPOL == 2 ? 2 : 4) pfb_analysis_low
         Dft<8, -1, float>::run(t);
 #pragma unroll
         for (int o2 = 0; o2 < 8; ++o2) {
-          const int c = o + 4 * (o1 + 8 * o2);       // X256[o + 4 k'], k' = o1 + 8 o2
-          const int ci = (c - a.chan_first) & 255;
-          if (live && ci < a.nchan_out) op[(long long)ci * NPOL] = t[o2];
+          if (FULL) {
+            if (live) op[4 * (o1 + 8 * o2) * NPOL] = t[o2];   // X256[o + 4 k'], k' = o1 + 8 o2
+          } else {
+            const int c = o + 4 * (o1 + 8 * o2);
+            const int ci = (c - a.chan_first) & 255;
+            if (live && ci < a.nchan_out) op[(long long)ci * NPOL] = t[o2];
+          }
         }
         if (o1 & 1) asm volatile("" ::: "memory");
       }
@@ -337,6 +343,65 @@ __global__ void __launch_bounds__(256, 3) pfb_chan_idft_low(const ChanArgs a) {
   }
 }
 
+// Dual-pol variant: one lane carries both polarisations of its 16 channels, so every global and
+// shared access is 128 bits wide (both pols of a channel are adjacent in TFP order) and the
+// inter-pass twiddles are shared by the two transforms.
+__global__ void __launch_bounds__(128, 4) pfb_chan_idft_low_p2(const ChanArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float4* ex = reinterpret_cast<float4*>(smem_raw);    // [2][8 rows][273] (pol0.re, pol0.im, pol1.re, pol1.im)
+  const int tid = threadIdx.x;
+  const int q = tid & 15, rsub = tid >> 4;
+  constexpr int ROWS = 8;
+  C tw[15];
+#pragma unroll
+  for (int o = 1; o < 16; ++o) {
+    float2 v = __ldg(a.tw256 + ((q * o) & 255));
+    tw[o - 1] = mk<float>(v.x, -v.y);
+  }
+  const long long npass = (a.nrows + ROWS - 1) / ROWS;
+  int buf = 0;
+  for (long long ps = blockIdx.x; ps < npass; ps += gridDim.x, buf ^= 1) {
+    const long long row = ps * ROWS + rsub;
+    float4* e = ex + (size_t)buf * ROWS * kColStride + (size_t)rsub * kColStride;
+    C x0[16], x1[16];
+    if (row < a.nrows) {
+      const float4* p = reinterpret_cast<const float4*>(a.in) + row * 256 + q;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float4 v = __ldg(p + i * 16);
+        x0[i] = mk<float>(v.x, v.y);
+        x1[i] = mk<float>(v.z, v.w);
+      }
+      fft_reg<4, 4, +1>(x0);
+      fft_reg<4, 4, +1>(x1);
+#pragma unroll
+      for (int o = 0; o < 16; ++o) {
+        C u0 = x0[slot<4, 4>(o)], u1 = x1[slot<4, 4>(o)];
+        if (o) { u0 = u0 * tw[o - 1]; u1 = u1 * tw[o - 1]; }
+        e[o * kQStride + q] = make_float4(u0.x, u0.y, u1.x, u1.y);
+      }
+    }
+    __syncthreads();
+    if (row < a.nrows) {
+      const int o = q;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float4 v = e[o * kQStride + i];
+        x0[i] = mk<float>(v.x, v.y);
+        x1[i] = mk<float>(v.z, v.w);
+      }
+      fft_reg<4, 4, +1>(x0);
+      fft_reg<4, 4, +1>(x1);
+      float4* p = reinterpret_cast<float4*>(a.out) + row * 256 + o;
+#pragma unroll
+      for (int o2 = 0; o2 < 16; ++o2) {
+        const C u0 = x0[slot<4, 4>(o2)], u1 = x1[slot<4, 4>(o2)];
+        p[o2 * 16] = make_float4(u0.x, u0.y, u1.x, u1.y);
+      }
+    }
+  }
+}
+
 // ===========================================================================
 // K3: per column: taper -> FFT256 -> keep 192 bins x weights -> IFFT192 -> keep middle
 // ===========================================================================
@@ -356,7 +421,9 @@ template <int NPOL> constexpr size_t res_smem_bytes() {
   return (size_t)2 * 16 * kColStride * sizeof(C) + (size_t)16 * 193 * sizeof(C) + 256 * sizeof(float);
 }
 
-template <int NPOL>
+// NCHAN > 0 / OV2 >= 0 bake the row pitch and the kept output range into the instruction stream
+// (immediate address offsets, pruned last butterfly stage); 0 / -1 read them from the arguments.
+template <int NPOL, int NCHAN, int OV2, bool FLIP>
 __global__ void __launch_bounds__(256, 2) pfb_resample_low(const ResArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   C* exA = reinterpret_cast<C*>(smem_raw);            // [16 cols][273]  phase 1 -> 2
@@ -366,10 +433,14 @@ __global__ void __launch_bounds__(256, 2) pfb_resample_low(const ResArgs a) {
   const int tid = threadIdx.x;
   const int c = tid & 15, q = tid >> 4;               // column, lane-in-transform
   constexpr int T1G = 16 / NPOL;                      // t1 values per CTA
-  const int groups = a.nchan / T1G;
+  const int nchan = NCHAN > 0 ? NCHAN : a.nchan;
+  const int ov2 = OV2 >= 0 ? OV2 : a.ov2;
+  const int keep = OV2 >= 0 ? 256 - 2 * (OV2 * 4 / 3) : a.keep;
+  const int keep2 = OV2 >= 0 ? 192 - 2 * OV2 : a.keep2;
+  const int groups = nchan / T1G;
   const int g = blockIdx.x % groups, sp = blockIdx.x / groups;
   const int t1_0 = g * T1G;
-  const long long rowlen = (long long)a.nchan * NPOL;
+  const int rowlen = nchan * NPOL;
   const int per = (a.nblk + a.nsplit - 1) / a.nsplit;
   const int n_begin = sp * per, n_end = min(a.nblk, n_begin + per);
 
@@ -395,15 +466,14 @@ __global__ void __launch_bounds__(256, 2) pfb_resample_low(const ResArgs a) {
   C* ocol = a.out + (long long)t1_0 * NPOL + c;
   C* eA = exA + c * kColStride;
   C* eB = exB + c * kColStride;
-  const float sgn_odd = a.flip ? -1.f : 1.f;
 
   for (int n = n_begin; n < n_end; ++n) {
     C x[16];
     {
       // phase 1: lane q holds tau = q + 16 i
-      const C* p = vcol + ((long long)n * a.keep + q) * rowlen;
+      const C* p = vcol + ((long long)n * keep + q) * rowlen;
 #pragma unroll
-      for (int i = 0; i < 16; ++i) x[i] = ld_nc(p + (long long)i * 16 * rowlen) * stp[q + 16 * i];
+      for (int i = 0; i < 16; ++i) x[i] = ld_nc(p + i * 16 * rowlen) * stp[q + 16 * i];
       fft_reg<4, 4, -1>(x);
 #pragma unroll
       for (int o = 0; o < 16; ++o) {
@@ -443,18 +513,20 @@ __global__ void __launch_bounds__(256, 2) pfb_resample_low(const ResArgs a) {
 #pragma unroll
       for (int i = 0; i < 16; ++i) x[i] = eB[m * kQStride + i];
       fft_reg<4, 4, +1>(x);
-      C* p = ocol + ((long long)n * a.keep2 - a.ov2 + m) * rowlen;
+      C* p = ocol + ((long long)n * keep2 - ov2 + m) * rowlen;
+      const bool odd = FLIP && (m & 1);          // t2 = m + 12 j has the parity of m
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
-        const int t2 = m + 12 * j;
-        if (t2 >= a.ov2 && t2 < 192 - a.ov2) {
+        // OV2 multiple of 12: the kept range is whole j's, decided at compile time
+        const bool keep_j = (OV2 >= 0 && OV2 % 12 == 0) ? (12 * j >= OV2 && 12 * j < 192 - OV2)
+                                                        : (m + 12 * j >= ov2 && m + 12 * j < 192 - ov2);
+        if (keep_j) {
           C v = x[slot<4, 4>(j)];
-          if ((t2 & 1) && a.flip) v = mk<float>(-v.x, -v.y);
-          p[(long long)(12 * j) * rowlen] = v;
+          if (odd) v = mk<float>(-v.x, -v.y);
+          p[12 * j * rowlen] = v;
         }
       }
     }
-    (void)sgn_odd;
   }
 }
 
@@ -586,18 +658,21 @@ inline int low_analysis_launch<float>(const AnalysisArgs& g, const void* d_low, 
   a.taps = h->taps; a.tw = h->tw;
   a.s0 = s0; a.n_local = n_eff; a.nblk = nblk; a.kout0 = g.kout0 + lo; a.L = (int)L;
   a.chan_first = g.chan_first; a.nchan_out = g.nchan_out;
-  cudaError_t e;
+  cudaError_t e = cudaSuccess;
+  const bool full = g.chan_first == 0 && g.nchan_out == 256;
+  auto go = [&](auto kernel, size_t smem, int threads) {
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return;
+    kernel<<<(unsigned)grid, threads, smem, st>>>(a);
+  };
   if (g.npol == 2) {
-    const size_t smem = low::ana_smem_bytes<2>();
-    e = cudaFuncSetAttribute(low::pfb_analysis_low<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    low::pfb_analysis_low<2><<<(unsigned)grid, 128, smem, st>>>(a);
+    if (full) go(low::pfb_analysis_low<2, true>, low::ana_smem_bytes<2>(), 128);
+    else go(low::pfb_analysis_low<2, false>, low::ana_smem_bytes<2>(), 128);
   } else {
-    const size_t smem = low::ana_smem_bytes<1>();
-    e = cudaFuncSetAttribute(low::pfb_analysis_low<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    low::pfb_analysis_low<1><<<(unsigned)grid, 64, smem, st>>>(a);
+    if (full) go(low::pfb_analysis_low<1, true>, low::ana_smem_bytes<1>(), 64);
+    else go(low::pfb_analysis_low<1, false>, low::ana_smem_bytes<1>(), 64);
   }
+  if (e != cudaSuccess) return (int)e;
   e = cudaGetLastError();
   if (e != cudaSuccess) return (int)e;
   *k_lo = lo;
@@ -660,7 +735,14 @@ inline int low_chan_idft_launch<float>(const void* d_low, const void* in, void* 
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   long long grid = npass < (long long)sms * 3 ? npass : (long long)sms * 3;
   cudaError_t e;
-  if (npol == 2) {
+  if (npol == 2 && ((uintptr_t)in % 16 == 0) && ((uintptr_t)out % 16 == 0)) {
+    const size_t smem2 = (size_t)2 * 8 * low::kColStride * sizeof(float4);
+    const long long npass2 = (nrows + 7) / 8;
+    const long long grid2 = npass2 < (long long)sms * 3 ? npass2 : (long long)sms * 3;
+    e = cudaFuncSetAttribute(low::pfb_chan_idft_low_p2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+    if (e != cudaSuccess) return (int)e;
+    low::pfb_chan_idft_low_p2<<<(unsigned)grid2, 128, smem2, st>>>(a);
+  } else if (npol == 2) {
     e = cudaFuncSetAttribute(low::pfb_chan_idft_low<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     low::pfb_chan_idft_low<2><<<(unsigned)grid, 256, smem, st>>>(a);
@@ -713,18 +795,23 @@ inline int low_resample_launch<float>(const void* d_low, const void* v, void* ou
   if (nsplit < 1) nsplit = 1;
   a.nsplit = (int)nsplit;
   const long long grid = nsplit * groups;
-  cudaError_t e;
+  cudaError_t e = cudaSuccess;
+  auto go = [&](auto kernel, size_t smem) {
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return;
+    kernel<<<(unsigned)grid, 256, smem, st>>>(a);
+  };
+  const bool low_shape = h->nchan == 256 && h->ov2 == 36;      // the SKA-Low PST configuration
   if (npol == 2) {
-    const size_t smem = low::res_smem_bytes<2>();
-    e = cudaFuncSetAttribute(low::pfb_resample_low<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    low::pfb_resample_low<2><<<(unsigned)grid, 256, smem, st>>>(a);
+    if (low_shape && !h->flip) go(low::pfb_resample_low<2, 256, 36, false>, low::res_smem_bytes<2>());
+    else if (h->flip) go(low::pfb_resample_low<2, 0, -1, true>, low::res_smem_bytes<2>());
+    else go(low::pfb_resample_low<2, 0, -1, false>, low::res_smem_bytes<2>());
   } else {
-    const size_t smem = low::res_smem_bytes<1>();
-    e = cudaFuncSetAttribute(low::pfb_resample_low<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    low::pfb_resample_low<1><<<(unsigned)grid, 256, smem, st>>>(a);
+    if (low_shape && !h->flip) go(low::pfb_resample_low<1, 256, 36, false>, low::res_smem_bytes<1>());
+    else if (h->flip) go(low::pfb_resample_low<1, 0, -1, true>, low::res_smem_bytes<1>());
+    else go(low::pfb_resample_low<1, 0, -1, false>, low::res_smem_bytes<1>());
   }
+  if (e != cudaSuccess) return (int)e;
   e = cudaGetLastError();
   if (e != cudaSuccess) return (int)e;
   *done = true;
