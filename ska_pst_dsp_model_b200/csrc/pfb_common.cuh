@@ -5,7 +5,9 @@
 
 namespace pfb {
 
-template <typename T> struct Cx { T x, y; };                 // interleaved re,im (DADA NDIM=2)
+// interleaved (re, im) as in the DADA payload (NDIM=2); aligned so that one complex moves as a single
+// 64-bit (fp32) / 128-bit (fp64) load or store
+template <typename T> struct alignas(2 * sizeof(T)) Cx { T x, y; };
 template <typename T> struct VecOf;
 template <> struct VecOf<float>  { using type = float2;  };
 template <> struct VecOf<double> { using type = double2; };
