@@ -402,6 +402,99 @@ __global__ void __launch_bounds__(128, 4) pfb_chan_idft_low_p2(const ChanArgs a)
   }
 }
 
+// TMA-fed variant of the dual-pol kernel: whole rows (4 KiB, contiguous in TFP order) are
+// streamed by cp.async.bulk into a 3-stage ring, so no warp ever waits on a global load, and
+// because the 16 lanes of a transform live in one warp the two passes exchange data through the
+// ring slot itself with __syncwarp() only - the CTA never executes a block-wide barrier.
+constexpr int kChanStages = 3;
+constexpr int kChanRows = 8;                      // rows per stage = 16 lanes x 8 = 128 threads
+__global__ void __launch_bounds__(128, 2) pfb_chan_idft_low_tma(const ChanArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float4* ring = reinterpret_cast<float4*>(smem_raw);                    // [stage][8 rows][273]
+  uint64_t* full = reinterpret_cast<uint64_t*>(ring + kChanStages * kChanRows * kColStride);
+  uint64_t* empty = full + kChanStages;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int q = tid & 15, rsub = tid >> 4;
+  const long long npass = (a.nrows + kChanRows - 1) / kChanRows;
+  // passes of this CTA: blockIdx.x, blockIdx.x + gridDim.x, ...
+  const long long my = npass > blockIdx.x ? (npass - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+  auto issue = [&](long long i) {                 // i-th pass of this CTA
+    const long long row0 = (blockIdx.x + i * gridDim.x) * kChanRows;
+    const int st = (int)(i % kChanStages);
+    long long nr = a.nrows - row0;
+    if (nr > kChanRows) nr = kChanRows;
+    mbar_expect_tx(&full[st], (uint32_t)(nr * 4096));
+    for (int r = 0; r < nr; ++r)
+      tma_load_1d(ring + ((size_t)st * kChanRows + r) * kColStride,
+                  reinterpret_cast<const char*>(a.in) + (row0 + r) * 4096, 4096, &full[st]);
+  };
+  if (tid == 0) {
+    for (int s = 0; s < kChanStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid == 0)
+    for (long long i = 0; i < kChanStages && i < my; ++i) issue(i);
+
+  C tw[15];
+#pragma unroll
+  for (int o = 1; o < 16; ++o) {
+    float2 v = __ldg(a.tw256 + ((q * o) & 255));
+    tw[o - 1] = mk<float>(v.x, -v.y);
+  }
+  for (long long i = 0; i < my; ++i) {
+    const int st = (int)(i % kChanStages);
+    if (tid == 0 && i >= 1 && i - 1 + kChanStages < my) {
+      mbar_wait(&empty[(i - 1) % kChanStages], (uint32_t)(((i - 1) / kChanStages) & 1));
+      issue(i - 1 + kChanStages);
+    }
+    mbar_wait(&full[st], (uint32_t)((i / kChanStages) & 1));
+    const long long row = (blockIdx.x + i * gridDim.x) * kChanRows + rsub;
+    float4* e = ring + ((size_t)st * kChanRows + rsub) * kColStride;
+    C x0[16], x1[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const float4 v = e[q + 16 * k];
+      x0[k] = mk<float>(v.x, v.y);
+      x1[k] = mk<float>(v.z, v.w);
+    }
+    __syncwarp();                                  // both rows of this warp fully read
+    fft_reg<4, 4, +1>(x0);
+    fft_reg<4, 4, +1>(x1);
+#pragma unroll
+    for (int o = 0; o < 16; ++o) {
+      C u0 = x0[slot<4, 4>(o)], u1 = x1[slot<4, 4>(o)];
+      if (o) { u0 = u0 * tw[o - 1]; u1 = u1 * tw[o - 1]; }
+      e[o * kQStride + q] = make_float4(u0.x, u0.y, u1.x, u1.y);
+    }
+    __syncwarp();
+    {
+      const int o = q;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        const float4 v = e[o * kQStride + k];
+        x0[k] = mk<float>(v.x, v.y);
+        x1[k] = mk<float>(v.z, v.w);
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // our generic-proxy writes vs the next TMA fill
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[st]);      // slot free for the TMA again
+      fft_reg<4, 4, +1>(x0);
+      fft_reg<4, 4, +1>(x1);
+      if (row < a.nrows) {
+        float4* p = reinterpret_cast<float4*>(a.out) + row * 256 + o;
+#pragma unroll
+        for (int o2 = 0; o2 < 16; ++o2) {
+          const C u0 = x0[slot<4, 4>(o2)], u1 = x1[slot<4, 4>(o2)];
+          p[o2 * 16] = make_float4(u0.x, u0.y, u1.x, u1.y);
+        }
+      }
+    }
+  }
+}
+
 // ===========================================================================
 // K3: per column: taper -> FFT256 -> keep 192 bins x weights -> IFFT192 -> keep middle
 // ===========================================================================
@@ -736,12 +829,12 @@ inline int low_chan_idft_launch<float>(const void* d_low, const void* in, void* 
   long long grid = npass < (long long)sms * 3 ? npass : (long long)sms * 3;
   cudaError_t e;
   if (npol == 2 && ((uintptr_t)in % 16 == 0) && ((uintptr_t)out % 16 == 0)) {
-    const size_t smem2 = (size_t)2 * 8 * low::kColStride * sizeof(float4);
-    const long long npass2 = (nrows + 7) / 8;
-    const long long grid2 = npass2 < (long long)sms * 3 ? npass2 : (long long)sms * 3;
-    e = cudaFuncSetAttribute(low::pfb_chan_idft_low_p2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+    const size_t smem2 = (size_t)low::kChanStages * low::kChanRows * low::kColStride * sizeof(float4) + 64;
+    const long long npass2 = (nrows + low::kChanRows - 1) / low::kChanRows;
+    const long long grid2 = npass2 < (long long)sms * 2 ? npass2 : (long long)sms * 2;
+    e = cudaFuncSetAttribute(low::pfb_chan_idft_low_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
     if (e != cudaSuccess) return (int)e;
-    low::pfb_chan_idft_low_p2<<<(unsigned)grid2, 128, smem2, st>>>(a);
+    low::pfb_chan_idft_low_tma<<<(unsigned)grid2, 128, smem2, st>>>(a);
   } else if (npol == 2) {
     e = cudaFuncSetAttribute(low::pfb_chan_idft_low<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
