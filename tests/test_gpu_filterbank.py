@@ -1,0 +1,112 @@
+"""GPU streaming classes (FilterBank.m / InverseFilterBank.m / TwoStage*.m mirrors) against the oracle classes."""
+import numpy as np
+import pytest
+
+from oracle import pfb_oracle as o
+
+pytestmark = pytest.mark.gpu
+
+
+def cn(rng, shape):
+    return (rng.standard_normal(shape) + 1j * rng.standard_normal(shape)).astype(np.complex64)
+
+
+def dev(a_pct):
+    import torch
+    a = np.ascontiguousarray(np.transpose(a_pct, (2, 1, 0)))
+    if a_pct.shape[1] == 1:
+        a = a[:, 0, :]
+    return torch.from_numpy(a).cuda()
+
+
+def host(t):
+    a = t.cpu().numpy()
+    if a.ndim == 2:
+        a = a[:, None, :]
+    return np.transpose(a, (2, 1, 0))
+
+
+def nerr(a, b):
+    return float(np.abs(a - b).max() / np.abs(b).max())
+
+
+def test_filterbank_streaming_low(pst_taps):
+    from ska_pst_dsp_model_b200.filterbank import FilterBank
+    rng = np.random.default_rng(1)
+    h = pst_taps / pst_taps.sum()
+    x = cn(rng, (2, 1, 3072 + 192 * 150))
+    ref_fb, fb = o.FilterBank(h, 256, "4/3"), FilterBank(h, 256, "4/3")
+    for a, b in [(0, 9000), (9000, 20000), (20000, x.shape[2])]:
+        r = ref_fb.execute(x[:, :, a:b].astype(np.complex128))
+        g = host(fb.execute(dev(x[:, :, a:b])))
+        assert g.shape == r.shape and g.shape[2] % 4 == 0
+        assert nerr(g, r) < 1e-5
+        assert fb.buffered_samples == ref_fb.buffered_samples
+
+
+def test_filterbank_rounding_options():
+    from ska_pst_dsp_model_b200.filterbank import FilterBank
+    rng = np.random.default_rng(2)
+    h = rng.standard_normal(81) / 9
+    x = cn(rng, (1, 1, 4000)) * 37.3
+    kw = dict(rnd_input=True, rms_input=20.0, rnd_output=True, rms_output=0.0)
+    r = o.FilterBank(h, 8, "8/7", **kw).execute(x.astype(np.complex128))
+    g = host(FilterBank(h, 8, "8/7", **kw).execute(dev(x)))
+    assert g.shape == r.shape
+    # integer-valued outputs; fp32 vs fp64 may flip a value that sits on a .5 boundary
+    assert np.all(g.real == np.round(g.real)) and np.mean(np.abs(g - r) > 0.5) < 2e-3
+
+
+def test_filterbank_lowcbf_first_call_flag(pst_taps):
+    from ska_pst_dsp_model_b200.filterbank import FilterBank
+    rng = np.random.default_rng(3)
+    x = cn(rng, (1, 1, 3072 + 192 * 40))
+    ref_fb = o.FilterBank(pst_taps, 256, "4/3", "polyphase_analysis_lowcbf")
+    fb = FilterBank(pst_taps, 256, "4/3", "polyphase_analysis_lowcbf")
+    for a, b in [(0, 6000), (6000, x.shape[2])]:
+        r = ref_fb.execute(x[:, :, a:b].astype(np.complex128))
+        g = host(fb.execute(dev(x[:, :, a:b])))
+        assert g.shape == r.shape and g.shape[1] == 216 and nerr(g, r) < 1e-5
+
+
+def test_inverse_filterbank_streaming():
+    from ska_pst_dsp_model_b200.filterbank import InverseFilterBank
+    rng = np.random.default_rng(4)
+    x = cn(rng, (2, 16, 48 * 9 + 40))
+    ref_i = o.InverseFilterBank(None, 64, 8, "4/3", "tukey")
+    gpu_i = InverseFilterBank(None, 64, 8, "4/3", "tukey")
+    for a, b in [(0, 200), (200, 360), (360, x.shape[2])]:
+        r = ref_i.execute(x[:, :, a:b].astype(np.complex128))
+        g = host(gpu_i.execute(dev(x[:, :, a:b])))
+        assert g.shape == r.shape and nerr(g, r) < 1e-5
+        assert gpu_i.buffered_samples == ref_i.buffered_samples
+
+
+def test_inverse_filterbank_rejects_spectral_taper_and_real_input():
+    import torch
+    from ska_pst_dsp_model_b200.filterbank import InverseFilterBank
+    from ska_pst_dsp_model_b200.lib import PfbError
+    with pytest.raises(PfbError):
+        InverseFilterBank(None, 64, 8, "4/3", "tukey", spectral_taper="hann")
+    with pytest.raises(ValueError):
+        InverseFilterBank(None, 64, 8, "4/3").execute(torch.zeros((100, 8, 1), device="cuda"))
+
+
+@pytest.mark.parametrize("critical,combine", [(False, 1), (True, 1), (True, 2)])
+def test_two_stage_round_trip_classes(critical, combine):
+    """test_sgcht.m options 4-8 in miniature: two-stage analysis (oversampled or critical) and the
+    stage-2 inversion with optional combine, class for class against the oracle."""
+    from ska_pst_dsp_model_b200.filterbank import TwoStageFilterBank, TwoStageInverseFilterBank
+    rng = np.random.default_rng(5)
+    h8 = o.design_pfb_fir_filter(8, "4/3", 6)
+    cfg = dict(filt_coeff=h8, n_chan=8, os_factor="4/3")
+    x = cn(rng, (1, 1, 6000))
+    ref = o.TwoStageFilterBank(cfg, critical=critical).execute(x.astype(np.complex128))
+    got = host(TwoStageFilterBank(cfg, critical=critical).execute(dev(x)))
+    assert got.shape == ref.shape and nerr(got, ref) < 1e-5
+    nch2 = 6 if critical else 8
+    icfg = dict(filt_coeff=h8, n_fft=24, overlap=4, os_factor="4/3")
+    r_inv = o.TwoStageInverseFilterBank(icfg, nch2=nch2, combine=combine).execute(ref.astype(np.complex128), stage2_nchan=8)
+    g_inv = host(TwoStageInverseFilterBank(icfg, nch2=nch2, stage2_nchan=8, combine=combine).execute(dev(ref)))
+    assert g_inv.shape == r_inv.shape and g_inv.shape[1] == 8 // combine
+    assert nerr(g_inv, r_inv) < 1e-5
