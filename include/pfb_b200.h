@@ -84,6 +84,10 @@ long long pfb_inverse_out_len(const pfb_inverse_plan* plan, long long n_dat); /*
 /* in: [n_dat][nchan][npol]; out: [out_len][npol] */
 int pfb_inverse_execute(pfb_inverse_plan* plan, const void* in_dev, void* out_dev, int npol,
                         long long n_dat, void* stream);
+/* spectral (frequency-domain) taper of polyphase_synthesis.m:282 / InverseFilterBank.frequency_taper:
+ * n = nchan*FN_width doubles multiplying the stitched spectrum (NULL clears it).  With a taper set
+ * the inversion runs the literal-order chain (per-channel FFT -> weights -> channel IDFT -> bin IFFT). */
+int pfb_inverse_set_spectral_taper(pfb_inverse_plan* plan, const double* taper, long long n);
 /* bytes of scratch between the two inversion kernels (default 128 MiB; <= ~64 MiB keeps it L2-resident) */
 int pfb_inverse_set_scratch_bytes(pfb_inverse_plan* plan, long long bytes);
 /* run only one stage of the chain over the whole input (profiling / roofline):

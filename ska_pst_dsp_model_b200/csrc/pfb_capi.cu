@@ -156,6 +156,10 @@ struct pfb_inverse_plan {
   const int* d_jmap = nullptr;
   const void* d_taper = nullptr;
   const void* d_wt = nullptr;
+  const void* d_wa = nullptr;        // literal chain: T[nchan][FNw] deripple x spectral taper
+  const void* d_wb = nullptr;        // literal chain: Cx<T>[nchan][FNw] stitch twiddle x gain
+  bool spectral = false;
+  std::vector<double> deripple_w;    // FN-order deripple weights (kept for set_spectral_taper)
   const void* d_low = nullptr;       // fast-path tables (pfb_low.cuh)
   bool low_fast = false;
   long long scratch_bytes = 128ll << 20;
@@ -393,6 +397,7 @@ static int inverse_build(pfb_inverse_plan* p, const double* taper, const double*
   const Cx<T>* dwt;
   if ((rc = p->tabs.upload(wt, &dwt))) return rc;
   p->d_wt = dwt;
+  p->deripple_w = w;
   if (p->combine > 1) {                                       // polyphase_synthesis.m:198-238
     std::vector<int> jm(p->nchan);
     const int per = p->nchan / p->combine;
@@ -567,6 +572,111 @@ static int inverse_run(pfb_inverse_plan* p, const void* in, void* out, int npol,
   return PFB_OK;
 }
 
+template <typename T> static int spectral_build(pfb_inverse_plan* p, const double* taper) {
+  const long long oN = (long long)p->nchan * p->FNw;
+  std::vector<T> wa((size_t)oN);
+  std::vector<Cx<T>> wb((size_t)oN);
+  const double g = ((double)p->de / p->nu) / (double)oN;
+  for (int ch = 0; ch < p->nchan; ++ch)
+    for (int r = 0; r < p->FNw; ++r) {
+      long long kk = ((long long)ch * p->FNw + r - p->off) % oN;          // polyphase_synthesis.m:253-278
+      if (kk < 0) kk += oN;
+      wa[(size_t)ch * p->FNw + r] = (T)(p->deripple_w[r] * taper[kk]);
+      double c, s;
+      unit((long long)(r - p->off) * ch, oN, +1, &c, &s);                  // here `ch` plays the role of t1
+      wb[(size_t)ch * p->FNw + r].x = (T)(g * c);
+      wb[(size_t)ch * p->FNw + r].y = (T)(g * s);
+    }
+  const T* dwa;
+  const Cx<T>* dwb;
+  int rc = p->tabs.upload(wa, &dwa);
+  if (rc) return rc;
+  if ((rc = p->tabs.upload(wb, &dwb))) return rc;
+  p->d_wa = dwa;
+  p->d_wb = dwb;
+  p->spectral = true;
+  return PFB_OK;
+}
+
+int pfb_inverse_set_spectral_taper(pfb_inverse_plan* p, const double* taper, long long n) {
+  if (!p) return fail(PFB_ERR_ARG, "null plan");
+  if (!taper) { p->spectral = false; return PFB_OK; }
+  if (n != (long long)p->nchan * p->FNw) return fail(PFB_ERR_ARG, "spectral taper must have nchan*FN_width = %lld points", (long long)p->nchan * p->FNw);
+  CU(cudaSetDevice(p->device));
+  return p->dtype == PFB_DTYPE_C64 ? spectral_build<float>(p, taper) : spectral_build<double>(p, taper);
+}
+
+// literal-order chain (spectral taper set): L1 -> K2g -> L3, chunked over blocks
+template <typename T>
+static int inverse_run_literal(pfb_inverse_plan* p, const void* in, void* out, int npol, long long n_dat, cudaStream_t st) {
+  const long long nblocks = pfb_inverse_nblocks(p, n_dat);
+  if (nblocks <= 0) return PFB_OK;
+  const long long rowlen = (long long)p->nchan * npol;
+  const long long blk_bytes = (long long)p->FNw * rowlen * sizeof(Cx<T>);
+  long long B = p->scratch_bytes / blk_bytes;
+  if (B < 1) B = 1;
+  if (B > nblocks) B = nblocks;
+  const size_t need = (size_t)(B * blk_bytes);
+  if (need > p->scratch_cap) {
+    if (p->d_scratch) CU(cudaFree(p->d_scratch));
+    p->d_scratch = nullptr; p->scratch_cap = 0;
+    CU(cudaMalloc(&p->d_scratch, need));
+    p->scratch_cap = need;
+  }
+  auto pick_tg = [&](size_t percol) {
+    int tg = 1;
+    while (p->nchan % (tg * 2) == 0 && (size_t)(tg * 2) * npol * percol <= 96 * 1024) tg *= 2;
+    return tg;
+  };
+  for (long long n0 = 0; n0 < nblocks; n0 += B) {
+    const long long nb = (nblocks - n0 < B) ? nblocks - n0 : B;
+    {
+      FwdSelArgs a;
+      memset(&a, 0, sizeof(a));
+      a.in = reinterpret_cast<const Cx<T>*>(in) + n0 * p->keep * rowlen;
+      a.z = p->d_scratch; a.fwd = p->fft_fwd; a.taper = p->d_taper; a.wa = p->d_wa; a.jmap = p->d_jmap;
+      a.nchan = p->nchan; a.npol = npol; a.Nf = p->Nf; a.FNw = p->FNw; a.keep = p->keep; a.d2 = p->d2;
+      const size_t percol = (size_t)padded_len<T>(p->Nf) * sizeof(Cx<T>);
+      a.tg = pick_tg(percol); a.nblk = (int)nb;
+      const size_t smem = (size_t)a.tg * npol * percol;
+      int rc = set_smem(pfb_fwd_select_generic<T>, smem);
+      if (rc) return rc;
+      pfb_fwd_select_generic<T><<<(unsigned)(nb * (p->nchan / a.tg)), 256, smem, st>>>(a);
+      if ((rc = check_launch("pfb_fwd_select_generic"))) return rc;
+    }
+    {
+      ChanIdftArgs a;
+      memset(&a, 0, sizeof(a));
+      a.in = p->d_scratch; a.out = p->d_scratch; a.fft = p->fft_chan; a.jmap = nullptr;
+      a.nchan = p->nchan; a.npol = npol; a.nrows = nb * p->FNw;
+      int rb = 4096 / (p->nchan * npol);
+      if (rb < 1) rb = 1;
+      a.rb = rb;
+      const size_t smem = (size_t)rb * npol * padded_len<T>(p->nchan) * sizeof(Cx<T>);
+      int rc = set_smem(pfb_chan_idft_generic<T>, smem);
+      if (rc) return rc;
+      pfb_chan_idft_generic<T><<<(unsigned)((a.nrows + rb - 1) / rb), 256, smem, st>>>(a);
+      if ((rc = check_launch("pfb_chan_idft_generic"))) return rc;
+    }
+    {
+      InvStoreArgs a;
+      memset(&a, 0, sizeof(a));
+      a.A = p->d_scratch;
+      a.out = reinterpret_cast<Cx<T>*>(out) + n0 * p->keep2 * rowlen;
+      a.bwd = p->fft_bwd; a.wb = p->d_wb;
+      a.nchan = p->nchan; a.npol = npol; a.FNw = p->FNw; a.ov2 = p->ov2; a.keep2 = p->keep2; a.off = p->off;
+      const size_t percol = (size_t)padded_len<T>(p->FNw) * sizeof(Cx<T>);
+      a.tg = pick_tg(percol); a.nblk = (int)nb;
+      const size_t smem = (size_t)a.tg * npol * percol;
+      int rc = set_smem(pfb_inv_store_generic<T>, smem);
+      if (rc) return rc;
+      pfb_inv_store_generic<T><<<(unsigned)(nb * (p->nchan / a.tg)), 256, smem, st>>>(a);
+      if ((rc = check_launch("pfb_inv_store_generic"))) return rc;
+    }
+  }
+  return PFB_OK;
+}
+
 int pfb_inverse_set_profiling(pfb_inverse_plan* p, int on) {
   if (!p) return fail(PFB_ERR_ARG, "null plan");
   p->profiling = on != 0;
@@ -597,6 +707,9 @@ int pfb_inverse_execute(pfb_inverse_plan* p, const void* in_dev, void* out_dev, 
   if (npol < 1 || npol > 2) return fail(PFB_ERR_ARG, "npol must be 1 or 2");
   CU(cudaSetDevice(p->device));
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (p->spectral)
+    return p->dtype == PFB_DTYPE_C64 ? inverse_run_literal<float>(p, in_dev, out_dev, npol, n_dat, st)
+                                     : inverse_run_literal<double>(p, in_dev, out_dev, npol, n_dat, st);
   return p->dtype == PFB_DTYPE_C64 ? inverse_run<float>(p, in_dev, out_dev, npol, n_dat, st)
                                    : inverse_run<double>(p, in_dev, out_dev, npol, n_dat, st);
 }

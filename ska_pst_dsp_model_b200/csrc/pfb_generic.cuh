@@ -190,4 +190,94 @@ __global__ void __launch_bounds__(256) pfb_resample_generic(const ResampleArgs a
   }
 }
 
+// ---------------------------------------------------------------------------
+// Literal-order chain, used only when a spectral (frequency-domain) taper is set
+// (InverseFilterBank.frequency_taper, polyphase_synthesis.m:282).  The taper multiplies the
+// stitched spectrum by a weight that depends on (channel, bin) jointly, so the channel IDFT
+// cannot be hoisted in front of the per-channel FFTs:
+//   L1 pfb_fwd_select_generic : per channel: taper -> Nf-FFT -> keep FNw bins x D[r] x T[kk]
+//   (K2g)                     : nchan-point inverse DFT across channels for every (block, bin)
+//   L3 pfb_inv_store_generic  : per output phase t1: x stitch twiddle x gain -> FNw-IFFT -> keep
+// ---------------------------------------------------------------------------
+struct FwdSelArgs {
+  const void* in;       // [tau][chan][pol]
+  void* z;              // [n][r][chan][pol]
+  FftDev fwd;
+  const void* taper;    // T[Nf]
+  const void* wa;       // T[nchan][FNw]  deripple x spectral taper (real)
+  const int* jmap;
+  int nchan, npol, Nf, FNw, keep, d2;
+  int tg, nblk;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) pfb_fwd_select_generic(const FwdSelArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  Cx<T>* sA = reinterpret_cast<Cx<T>*>(smem_raw);
+  const int ncol = a.tg * a.npol, ldA = padded_len<T>(a.Nf);
+  const int groups = a.nchan / a.tg;
+  const int g = blockIdx.x % groups;
+  const long long nb = blockIdx.x / groups;
+  const int ch0 = g * a.tg;
+  const long long rowlen = (long long)a.nchan * a.npol;
+  const Cx<T>* __restrict__ u = reinterpret_cast<const Cx<T>*>(a.in) + nb * a.keep * rowlen;
+  const T* __restrict__ taper = reinterpret_cast<const T*>(a.taper);
+  for (int e = threadIdx.x; e < a.Nf * ncol; e += blockDim.x) {
+    const int col = e % ncol, tau = e / ncol;
+    const int ch = ch0 + col / a.npol, pol = col % a.npol;
+    const int src = a.jmap ? __ldg(a.jmap + ch) : ch;
+    sA[(size_t)col * ldA + padi<T>(tau)] = ldg_cx<T>(u + tau * rowlen + (long long)src * a.npol + pol) * __ldg(taper + tau);
+  }
+  __syncthreads();
+  fft_smem<T, -1, false>(sA, ldA, ncol, a.fwd);
+  const T* __restrict__ wa = reinterpret_cast<const T*>(a.wa);
+  Cx<T>* __restrict__ z = reinterpret_cast<Cx<T>*>(a.z) + nb * a.FNw * rowlen;
+  for (int e = threadIdx.x; e < a.FNw * ncol; e += blockDim.x) {
+    const int col = e % ncol, r = e / ncol;
+    const int ch = ch0 + col / a.npol, pol = col % a.npol;
+    int b = r + a.d2 + a.Nf / 2;
+    if (b >= a.Nf) b -= a.Nf;
+    z[(long long)r * rowlen + (long long)ch * a.npol + pol] =
+        sA[(size_t)col * ldA + padi<T>(__ldg(a.fwd.perm + b))] * __ldg(wa + (size_t)ch * a.FNw + r);
+  }
+}
+
+struct InvStoreArgs {
+  const void* A;        // [n][r][t1][pol]
+  void* out;            // [T2][t1][pol]
+  FftDev bwd;
+  const void* wb;       // Cx<T>[nchan][FNw]: gain x exp(2 pi i (r-off) t1 / oN)
+  int nchan, npol, FNw, ov2, keep2, off;
+  int tg, nblk;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) pfb_inv_store_generic(const InvStoreArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  Cx<T>* sB = reinterpret_cast<Cx<T>*>(smem_raw);
+  const int ncol = a.tg * a.npol, ldB = padded_len<T>(a.FNw);
+  const int groups = a.nchan / a.tg;
+  const int g = blockIdx.x % groups;
+  const long long nb = blockIdx.x / groups;
+  const int t1_0 = g * a.tg;
+  const long long rowlen = (long long)a.nchan * a.npol;
+  const Cx<T>* __restrict__ A = reinterpret_cast<const Cx<T>*>(a.A) + nb * a.FNw * rowlen + (long long)t1_0 * a.npol;
+  const Cx<T>* __restrict__ wb = reinterpret_cast<const Cx<T>*>(a.wb);
+  for (int e = threadIdx.x; e < a.FNw * ncol; e += blockDim.x) {
+    const int col = e % ncol, r = e / ncol;
+    const int t1 = t1_0 + col / a.npol;
+    int rp = r - a.off;
+    if (rp < 0) rp += a.FNw;
+    sB[(size_t)col * ldB + padi<T>(__ldg(a.bwd.perm + rp))] =
+        ldg_cx<T>(A + (long long)r * rowlen + col) * ldg_cx<T>(wb + (size_t)t1 * a.FNw + r);
+  }
+  __syncthreads();
+  fft_smem<T, +1, true>(sB, ldB, ncol, a.bwd);
+  Cx<T>* __restrict__ out = reinterpret_cast<Cx<T>*>(a.out) + nb * a.keep2 * rowlen + (long long)t1_0 * a.npol;
+  for (int e = threadIdx.x; e < a.keep2 * ncol; e += blockDim.x) {
+    const int col = e % ncol, i = e / ncol;
+    out[i * rowlen + col] = sB[(size_t)col * ldB + padi<T>(i + a.ov2)];
+  }
+}
+
 }  // namespace pfb

@@ -89,8 +89,9 @@ class InverseFilterBank:
     def __init__(self, filt_coeff, n_fft, overlap, os_factor, temporal_taper="tukey", critical=False, combine=1,
                  sample_offset=0, spectral_taper=None, dtype=None, device=None):
         torch = _torch()
-        if spectral_taper not in (None, "no_window", "identity"):
-            raise PfbError("spectral (frequency) taper is not implemented on the GPU path yet (pfb_b200 error -3)")
+        if spectral_taper not in (None, "no_window", "identity", "hann"):
+            raise PfbError(f"unknown spectral taper {spectral_taper!r}")
+        self.spectral_taper = spectral_taper if spectral_taper == "hann" else None
         self.filt_coeff = filt_coeff
         self.n_fft, self.overlap = int(n_fft), int(overlap)
         self.os_factor = Rational.from_str(os_factor)
@@ -109,6 +110,8 @@ class InverseFilterBank:
             self._plans[key] = ops.InversePlan(nchan, self.os_factor, self.n_fft, self.overlap, self.temporal_taper,
                                                deripple_taps=None, spans_nyquist=not self.critical,
                                                combine=self.combine, dtype=self.dtype, device=self.device)
+            if self.spectral_taper:
+                self._plans[key].set_spectral_taper(self.spectral_taper)
         return self._plans[key]
 
     def execute(self, x):

@@ -168,6 +168,21 @@ class InversePlan:
                                                 _stream_ptr(self.device)))
         return out
 
+    def set_spectral_taper(self, taper):
+        """Real window of nchan*FN_width points on the stitched spectrum (polyphase_synthesis.m:282);
+        ``"hann"`` builds circshift(hann(len), len/2) as PFBWindow.m:79-94 does; None clears it."""
+        if taper is None:
+            _l.check(_l.lib.pfb_inverse_set_spectral_taper(self._h, None, 0))
+            return
+        n = self.nchan * self.fn_width
+        if isinstance(taper, str):
+            if taper != "hann":
+                raise KeyError(f"unknown spectral taper {taper!r}")
+            from .fft_windows import hann_window
+            taper = np.roll(hann_window(n), n // 2)
+        keep, ptr = _dptr(taper)
+        _l.check(_l.lib.pfb_inverse_set_spectral_taper(self._h, ptr, keep.size))
+
     def set_profiling(self, on=True):
         _l.check(_l.lib.pfb_inverse_set_profiling(self._h, int(on)))
 

@@ -82,12 +82,18 @@ def test_inverse_filterbank_streaming():
         assert gpu_i.buffered_samples == ref_i.buffered_samples
 
 
-def test_inverse_filterbank_rejects_spectral_taper_and_real_input():
+def test_inverse_filterbank_spectral_taper_and_real_input():
+    """frequency_taper('hann') (InverseFilterBank.m:48-61) runs the literal-order chain on the GPU."""
     import torch
     from ska_pst_dsp_model_b200.filterbank import InverseFilterBank
     from ska_pst_dsp_model_b200.lib import PfbError
+    rng = np.random.default_rng(6)
+    x = cn(rng, (2, 16, 48 * 6 + 16))
+    r = o.InverseFilterBank(None, 64, 8, "4/3", "tukey", spectral_taper="hann").execute(x.astype(np.complex128))
+    g = host(InverseFilterBank(None, 64, 8, "4/3", "tukey", spectral_taper="hann").execute(dev(x)))
+    assert g.shape == r.shape and nerr(g, r) < 1e-5
     with pytest.raises(PfbError):
-        InverseFilterBank(None, 64, 8, "4/3", "tukey", spectral_taper="hann")
+        InverseFilterBank(None, 64, 8, "4/3", "tukey", spectral_taper="blackman")
     with pytest.raises(ValueError):
         InverseFilterBank(None, 64, 8, "4/3").execute(torch.zeros((100, 8, 1), device="cuda"))
 

@@ -163,6 +163,35 @@ def test_inversion_chunked_scratch_and_offset(dt, pst_taps):
     assert nerr(got, ref) < TOL[dt]
 
 
+@pytest.mark.parametrize("dt", ["c64", "c128"])
+@pytest.mark.parametrize("nchan,osf,nfft,ov,spans,comb,dr", [
+    (256, "4/3", 256, 48, True, 1, True),
+    (16, "4/3", 48, 12, False, 4, False),
+    (8, "8/7", 64, 8, True, 1, True),
+    (192, "4/3", 128, 16, False, 1, False),
+])
+def test_inversion_spectral_taper(nchan, osf, nfft, ov, spans, comb, dr, dt, pst_taps):
+    """polyphase_synthesis.m:282 with the hann spectral taper (literal-order chain)."""
+    from ska_pst_dsp_model_b200 import ops
+    rng = np.random.default_rng(nchan + nfft)
+    os_ = o.OSFactor.from_str(osf)
+    x = cnoise(rng, (2, nchan, (nfft - 2 * ov) * 3 + 2 * ov + 3))
+    h = None
+    if dr:
+        h = pst_taps / pst_taps.sum() if nchan == 256 else _lowpass(nchan)
+    fnw = nfft * os_.de // os_.nu
+    st = o.spectral_hann(nchan * fnw)
+    ref = o.polyphase_synthesis(x, spans, nfft, osf, h, 1, ov, o.window_tukey(nfft, ov), st, comb)
+    plan = ops.InversePlan(nchan, osf, nfft, ov, "tukey", deripple_taps=h, spans_nyquist=spans, combine=comb,
+                           dtype=tdtype(dt))
+    plan.set_spectral_taper("hann")
+    got = from_dev(plan(to_dev(x, dt)))
+    assert got.shape == ref.shape and nerr(got, ref) < TOL[dt]
+    plan.set_spectral_taper(None)                       # back to the factored chain
+    ref0 = o.polyphase_synthesis(x, spans, nfft, osf, h, 1, ov, o.window_tukey(nfft, ov), None, comb)
+    assert nerr(from_dev(plan(to_dev(x, dt))), ref0) < TOL[dt]
+
+
 def test_round_trip_impulse_criteria(pst_taps):
     """TestImpulse.m:46-73 on the GPU chain: peak where sgcht.m:466-473 puts it,
     everything else below -60 dB."""
