@@ -103,6 +103,18 @@ int pfb_inverse_execute_stage(pfb_inverse_plan* plan, int stage, const void* in_
 int pfb_inverse_set_profiling(pfb_inverse_plan* plan, int on);
 int pfb_inverse_get_profile(pfb_inverse_plan* plan, double* ms2, long long* launches2);
 
+/* ---- on-device test vectors and purity reductions (python/data_gen/generate_test_vector.py:24-71,
+ *      python/verify/util.py:15-43, purity.py:154-160).
+ * kind 0: time_domain_impulse(n, offset=p0, width=p1); kind 1: complex_sinusoid(n, freq=p0 [bins],
+ * phase=p1 [rad], bin_offset=p2); every polarisation gets the same signal; out: [n][npol]. */
+int pfb_generate_test_vector(int kind, void* out_dev, long long n, int npol, int dtype, double p0,
+                             double p1, double p2, void* stream);
+/* args_dev: device array of nvec records {const void* a; const void* b; long long n, stride_a, stride_b;
+ * double scale_b; double* out;} (56 bytes each).  For every record one CTA reduces the series b (and the
+ * reference a, may be NULL) and writes out[0..7] = sum|b-a|, max|b-a|, sum|b|^2, largest |b|^2,
+ * second largest |b|^2, argmax, sum|b|, n. */
+int pfb_purity_metrics(const void* args_dev, int nvec, int dtype, void* stream);
+
 /* kernels launched by this library since load (bench.py "gpu_launches") */
 long long pfb_launch_count(void);
 

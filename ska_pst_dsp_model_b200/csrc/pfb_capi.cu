@@ -13,6 +13,7 @@
 #include "../../include/pfb_b200.h"
 #include "pfb_generic.cuh"
 #include "pfb_low.cuh"
+#include "pfb_purity.cuh"
 
 using namespace pfb;
 
@@ -731,3 +732,30 @@ int pfb_inverse_execute_stage(pfb_inverse_plan* p, int stage, const void* in_dev
   return fail(PFB_ERR_ARG, "stage must be 0 or 1");
 }
 
+// ---------------------------------------------------------------------------
+// test vectors + purity reductions on device
+int pfb_generate_test_vector(int kind, void* out_dev, long long n, int npol, int dtype, double p0, double p1, double p2,
+                             void* stream) {
+  if (!out_dev || n < 0 || npol < 1 || (kind != 0 && kind != 1)) return fail(PFB_ERR_ARG, "pfb_generate_test_vector: bad argument");
+  if (n == 0) return PFB_OK;
+  GenArgs a;
+  a.out = out_dev; a.n = n; a.npol = npol; a.kind = kind; a.p0 = p0; a.p1 = p1; a.p2 = p2;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  long long grid = (n + 255) / 256;
+  if (grid > 148 * 16) grid = 148 * 16;
+  if (dtype == PFB_DTYPE_C64) pfb_generate_kernel<float><<<(unsigned)grid, 256, 0, st>>>(a);
+  else if (dtype == PFB_DTYPE_C128) pfb_generate_kernel<double><<<(unsigned)grid, 256, 0, st>>>(a);
+  else return fail(PFB_ERR_ARG, "dtype must be 0 (c64) or 1 (c128)");
+  return check_launch("pfb_generate_kernel");
+}
+
+int pfb_purity_metrics(const void* args_dev, int nvec, int dtype, void* stream) {
+  if (!args_dev || nvec < 0) return fail(PFB_ERR_ARG, "pfb_purity_metrics: bad argument");
+  if (nvec == 0) return PFB_OK;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const MetricsArgs* a = reinterpret_cast<const MetricsArgs*>(args_dev);
+  if (dtype == PFB_DTYPE_C64) pfb_metrics_kernel<float><<<nvec, 1024, 0, st>>>(a);
+  else if (dtype == PFB_DTYPE_C128) pfb_metrics_kernel<double><<<nvec, 1024, 0, st>>>(a);
+  else return fail(PFB_ERR_ARG, "dtype must be 0 (c64) or 1 (c128)");
+  return check_launch("pfb_metrics_kernel");
+}

@@ -1,0 +1,113 @@
+// Test-vector synthesis and purity reductions on the device:
+//   K6 pfb_generate_kernel : time_domain_impulse / complex_sinusoid of
+//      python/data_gen/generate_test_vector.py:24-71 written straight into the analysis input
+//   K5 pfb_metrics_kernel  : the reductions of python/verify/util.py:15-43 and purity.py:154-160
+//      (|x|^2, zero the maximum, max / total spurious; |b - a| sum) in one pass per vector
+#pragma once
+#include "pfb_common.cuh"
+
+namespace pfb {
+
+struct GenArgs {
+  void* out;            // [n][npol] complex
+  long long n;
+  int npol, kind;       // 0 impulse, 1 tone
+  double p0, p1, p2;    // impulse: offset, width;  tone: frequency (bins), phase (rad), bin offset
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) pfb_generate_kernel(const GenArgs a) {
+  Cx<T>* out = reinterpret_cast<Cx<T>*>(a.out);
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < a.n; t += (long long)gridDim.x * blockDim.x) {
+    Cx<T> v = mk<T>((T)0, (T)0);
+    if (a.kind == 0) {
+      const long long o = (long long)a.p0, w = (long long)a.p1;
+      if (t >= o && t < o + w) v.x = (T)1;
+    } else {
+      // exp(i (2 pi (f + bin_offset) t / n + phase)), evaluated in double like numpy
+      const double cyc = (a.p0 + a.p2) * (double)t / (double)a.n;
+      const double ang = 2.0 * 3.14159265358979323846 * (cyc - floor(cyc)) + a.p1;
+      double s, c;
+      sincos(ang, &s, &c);
+      v.x = (T)c;
+      v.y = (T)s;
+    }
+    for (int p = 0; p < a.npol; ++p) out[t * a.npol + p] = v;
+  }
+}
+
+struct MetricsArgs {
+  const void* a;        // reference series (may be null), complex, element stride `stride`
+  const void* b;        // series under test
+  long long n;
+  long long stride_a, stride_b;
+  double scale_b;       // b is multiplied by this before use (purity.py divides by fft_size)
+  double* out;          // [8]: sum|b-a|, max|b-a|, sum p, max1 p, max2 p, argmax, sum|b|, n
+};
+
+struct Top2 {
+  double m1, m2;
+  long long i1;
+};
+__device__ __forceinline__ Top2 merge(Top2 x, Top2 y) {
+  Top2 r;
+  if (x.m1 > y.m1 || (x.m1 == y.m1 && x.i1 <= y.i1)) { r.m1 = x.m1; r.i1 = x.i1; r.m2 = fmax(x.m2, y.m1); }
+  else { r.m1 = y.m1; r.i1 = y.i1; r.m2 = fmax(y.m2, x.m1); }
+  return r;
+}
+
+// one CTA per vector (grid = number of vectors; args array indexed by blockIdx.x)
+template <typename T>
+__global__ void __launch_bounds__(1024) pfb_metrics_kernel(const MetricsArgs* args) {
+  const MetricsArgs a = args[blockIdx.x];
+  const Cx<T>* pa = reinterpret_cast<const Cx<T>*>(a.a);
+  const Cx<T>* pb = reinterpret_cast<const Cx<T>*>(a.b);
+  double sdiff = 0, mdiff = 0, spow = 0, sabs = 0;
+  Top2 t2{-1.0, -1.0, 0};
+  for (long long i = threadIdx.x; i < a.n; i += blockDim.x) {
+    const Cx<T> vb = pb[i * a.stride_b];
+    const double br = (double)vb.x * a.scale_b, bi = (double)vb.y * a.scale_b;
+    const double p = br * br + bi * bi;
+    spow += p;
+    sabs += sqrt(p);
+    Top2 one{p, -1.0, i};
+    t2 = merge(t2, one);
+    if (pa) {
+      const Cx<T> va = pa[i * a.stride_a];
+      const double dr = br - (double)va.x * a.scale_b, di = bi - (double)va.y * a.scale_b;
+      const double d = sqrt(dr * dr + di * di);
+      sdiff += d;
+      mdiff = fmax(mdiff, d);
+    }
+  }
+  __shared__ double sh[5][32];
+  __shared__ long long shi[32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int o = 16; o > 0; o >>= 1) {
+    sdiff += __shfl_down_sync(0xffffffff, sdiff, o);
+    mdiff = fmax(mdiff, __shfl_down_sync(0xffffffff, mdiff, o));
+    spow += __shfl_down_sync(0xffffffff, spow, o);
+    sabs += __shfl_down_sync(0xffffffff, sabs, o);
+    Top2 y{__shfl_down_sync(0xffffffff, t2.m1, o), __shfl_down_sync(0xffffffff, t2.m2, o),
+           __shfl_down_sync(0xffffffff, t2.i1, o)};
+    t2 = merge(t2, y);
+  }
+  if (lane == 0) { sh[0][warp] = sdiff; sh[1][warp] = mdiff; sh[2][warp] = spow; sh[3][warp] = t2.m1; sh[4][warp] = t2.m2; shi[warp] = t2.i1; }
+  __shared__ double shabs[32];
+  if (lane == 0) shabs[warp] = sabs;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int nw = (blockDim.x + 31) / 32;
+    double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+    Top2 t{-1.0, -1.0, 0};
+    for (int w = 0; w < nw; ++w) {
+      s0 += sh[0][w]; s1 = fmax(s1, sh[1][w]); s2 += sh[2][w]; s3 += shabs[w];
+      Top2 y{sh[3][w], sh[4][w], shi[w]};
+      t = merge(t, y);
+    }
+    a.out[0] = s0; a.out[1] = s1; a.out[2] = s2; a.out[3] = t.m1; a.out[4] = t.m2 < 0 ? 0.0 : t.m2;
+    a.out[5] = (double)t.i1; a.out[6] = s3; a.out[7] = (double)a.n;
+  }
+}
+
+}  // namespace pfb

@@ -103,3 +103,48 @@ def test_purity_driver_meets_requirement(tmp_path, pst_taps):
     rep = json.load(open(path))
     assert set(rep["test_time_domain_impulse"][0]) == {"mean_diff", "total_diff", "max_spurious_power",
                                                         "total_spurious_power", "mean_spurious_power", "arg"}
+
+
+def test_batch_purity_matches_file_driver(tmp_path, pst_taps):
+    """The on-device batched sweep reproduces the file-based purity driver's metrics."""
+    from ska_pst_dsp_model_b200 import data_gen
+    from ska_pst_dsp_model_b200.batch import BatchPurity
+    from ska_pst_dsp_model_b200.verify.purity import TestPurity
+    data_gen.set_config("low_pst")
+    h = pst_taps / pst_taps.sum()
+    norm = tmp_path / "taps.npy"
+    np.save(norm, h)
+    t = TestPurity(n_test=4, os_factor="4/3", input_fft_length=256, input_overlap=48, fft_window="tukey", deripple=True,
+                   channels=256, fir_filter_taps=3072, fir_filter_coeff_file_path=str(norm), blocks=3,
+                   output_dir=str(tmp_path))
+    offs, freqs = np.array([12000, 40000, 70000]), np.array([3, 300, 49152 * 3 // 2])
+    t.time_domain_args["offset"], t.freq_domain_args["frequency"] = offs, freqs
+    t.temporal_purity()
+    t.spectral_purity()
+    bp = BatchPurity("4/3", 256, 48, "tukey", True, 256, h, 3, vectors_per_batch=2)
+    assert bp.total_sample_shift == t.total_sample_shift and bp.n_samples == t.n_samples
+    got_t, got_f = bp.temporal(offs), bp.spectral(freqs)
+    for key, got in (("test_time_domain_impulse", got_t), ("test_complex_sinusoid", got_f)):
+        for r, g in zip(t.report[key], got):
+            assert r["arg"] == g["arg"]
+            assert abs(r["total_diff"] - g["total_diff"]) <= 2e-3 * abs(r["total_diff"]) + 1e-6
+            # the file driver reads taps back from COEFF_0 (%0.6E) for the deripple: dB values agree to a fraction of a dB
+            for k in ("max_spurious_power", "total_spurious_power", "mean_spurious_power"):
+                assert abs(r[k] - g[k]) < 1.0, (key, k, r[k], g[k])
+            assert g["max_spurious_power"] < -60
+
+
+def test_device_generators_match_reference_definitions():
+    import ctypes
+    import torch
+    from ska_pst_dsp_model_b200 import data_gen
+    from ska_pst_dsp_model_b200 import lib as L
+    n = 5000
+    x = torch.empty((n, 2), dtype=torch.complex64, device="cuda")
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    L.check(L.lib.pfb_generate_test_vector(0, x.data_ptr(), n, 2, 0, 1234.0, 3.0, 0.0, st))
+    ref = data_gen.time_domain_impulse(n, [1234], [3])
+    assert np.array_equal(x.cpu().numpy()[:, 0], ref) and np.array_equal(x.cpu().numpy()[:, 1], ref)
+    L.check(L.lib.pfb_generate_test_vector(1, x.data_ptr(), n, 2, 0, 37.0, np.pi / 4, 0.1, st))
+    ref = data_gen.complex_sinusoid(n, [37], [np.pi / 4], 0.1)
+    assert np.abs(x.cpu().numpy()[:, 1] - ref).max() < 2e-7
