@@ -69,7 +69,7 @@ class AnalysisPlan:
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
-        if h:
+        if h and _l is not None and getattr(_l, "lib", None) is not None:     # (module may be gone at interpreter exit)
             _l.lib.pfb_analysis_plan_destroy(h)
 
     def nblocks(self, n_dat, first_call=True):
@@ -136,7 +136,7 @@ class InversePlan:
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
-        if h:
+        if h and _l is not None and getattr(_l, "lib", None) is not None:
             _l.lib.pfb_inverse_plan_destroy(h)
 
     def nblocks(self, n_dat):

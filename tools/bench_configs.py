@@ -1,0 +1,78 @@
+#!/usr/bin/env python
+"""Timings of the other BASELINE configs (parity-test cases, not the bench line):
+cfg1 (8 ch, 8/7, PST taps, 2^18 impulse), cfg3 (Mid: 4096 ch, 8/7, 100 353-tap two-stage design,
+padded analysis + inversion Nf=512/ov=128), cfg5 (batched purity sweep)."""
+import json
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+import numpy as np
+import torch
+
+from ska_pst_dsp_model_b200 import ops
+from ska_pst_dsp_model_b200.batch import BatchPurity
+from ska_pst_dsp_model_b200.filters import design_pfb_fir_filter_two_stage, load_pst_taps
+
+
+def timeit(fn, reps=5):
+    fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+res = {}
+h = load_pst_taps(normalise=True)
+# cfg1
+n = 1 << 18
+x = torch.zeros((n, 1), dtype=torch.complex64, device="cuda")
+x[int(0.11 * n)] = 1
+ana = ops.AnalysisPlan(8, "8/7", h)
+inv = ops.InversePlan(8, "8/7", 256, 48, "tukey", deripple_taps=h)
+ms_a = timeit(lambda: ana(x))
+ch = ana(x)
+ms_i = timeit(lambda: inv(ch))
+res["cfg1"] = {"shape": "8 ch, OS 8/7, 3072 taps, 2^18 x 1 pol", "analysis_ms": ms_a, "inversion_ms": ms_i,
+               "analysis_Msamples_s": n / ms_a / 1e3, "round_trip_Msamples_s": n / (ms_a + ms_i) / 1e3,
+               "kernels": "generic (FMA-bound: 384 taps/arm)"}
+# cfg3 (Mid)
+if "--skip-mid" not in sys.argv:
+    t0 = time.time()
+    hm = design_pfb_fir_filter_two_stage(4096, 8, 7)
+    t_design = time.time() - t0
+    n = 1 << 22
+    xm = torch.view_as_complex(torch.randn((n, 2, 2), device="cuda"))
+    ana = ops.AnalysisPlan(4096, "8/7", hm, "polyphase_analysis_padded")
+    t0 = time.time()
+    inv = ops.InversePlan(4096, "8/7", 512, 128, "tukey", deripple_taps=hm)
+    t_plan = time.time() - t0
+    ms_a = timeit(lambda: ana(xm), 2)
+    chm = ana(xm)
+    ms_i = timeit(lambda: inv(chm), 2)
+    res["cfg3"] = {"shape": f"4096 ch, OS 8/7, {hm.size} taps (padded), Nf=512, ov=128, 2^22 x 2 pol",
+                   "filter_design_s": t_design, "inverse_plan_s": t_plan, "analysis_ms": ms_a, "inversion_ms": ms_i,
+                   "analysis_Msamples_s": 2 * n / ms_a / 1e3, "round_trip_Msamples_s": 2 * n / (ms_a + ms_i) / 1e3,
+                   "nblocks": int(chm.shape[0]), "kernels": "generic"}
+    del xm, chm, ana, inv
+# cfg5: batched purity sweep
+nvec = int(os.environ.get("NVEC", "512"))
+bp = BatchPurity("4/3", 256, 48, "tukey", True, 256, h, 3, vectors_per_batch=32)
+bp.sweep(8, 3)
+torch.cuda.synchronize()
+t0 = time.time()
+rep = bp.sweep(nvec, 3)
+torch.cuda.synchronize()
+dt = time.time() - t0
+worst_t = max(r["max_spurious_power"] for r in rep["test_time_domain_impulse"][:-1])
+worst_f = max(r["max_spurious_power"] for r in rep["test_complex_sinusoid"])
+res["cfg5"] = {"shape": f"{2 * nvec} vectors of 147456 samples (impulse + tone sweep, purity.py grid)",
+               "seconds": dt, "vectors_per_s": 2 * nvec / dt, "Msamples_s": 2 * nvec * 147456 / dt / 1e6,
+               "worst_max_spurious_dB_time": worst_t, "worst_max_spurious_dB_freq": worst_f}
+print(json.dumps(res, indent=1))
