@@ -22,6 +22,7 @@
 //    lanes per transform with in-register radix-16/12 butterflies and compile-time twiddles.
 #pragma once
 #include <cstdlib>
+#include <type_traits>
 #include <vector>
 
 #include "pfb_generic.cuh"
@@ -512,7 +513,8 @@ struct ResArgs {
 };
 
 template <int COLS> constexpr size_t res_smem_bytes() {
-  return (size_t)2 * COLS * kColStride * sizeof(C) + (size_t)COLS * 193 * sizeof(C) + 256 * sizeof(float);
+  return (size_t)2 * COLS * kColStride * sizeof(C) + (size_t)COLS * 193 * sizeof(C) + (256 + 192) * sizeof(C) +
+         256 * sizeof(float);
 }
 
 // NCHAN > 0 / OV2 >= 0 bake the row pitch and the kept output range into the instruction stream
@@ -524,7 +526,9 @@ __global__ void __launch_bounds__(16 * COLS, 512 / (16 * COLS)) pfb_resample_low
   C* exA = reinterpret_cast<C*>(smem_raw);            // [COLS][273]  phase 1 -> 2
   C* exB = exA + COLS * kColStride;                   // [COLS][273]  phase 2 -> 3 ([m][o] stride 17)
   C* swt = exB + COLS * kColStride;                   // [COLS][193]  weights of this column group
-  float* stp = reinterpret_cast<float*>(swt + COLS * 193);
+  C* t1s = swt + COLS * 193;                          // [16 o][16 q]  exp(-2 pi i q o / 256)
+  C* t2s = t1s + 256;                                 // [12 m][16 o]  exp(+2 pi i o m / 192)
+  float* stp = reinterpret_cast<float*>(t2s + 192);
   const int tid = threadIdx.x;
   const int c = tid % COLS, q = tid / COLS;           // column, lane-in-transform
   constexpr int T1G = COLS / NPOL;                    // t1 values per CTA
@@ -544,16 +548,15 @@ __global__ void __launch_bounds__(16 * COLS, 512 / (16 * COLS)) pfb_resample_low
     swt[cc * 193 + rr] = a.wt[(size_t)(t1_0 + cc / NPOL) * 192 + rr];
   }
   for (int i = tid; i < 256; i += 16 * COLS) stp[i] = a.taper[i];
-  C tw1[15], tw2[11];
-#pragma unroll
-  for (int o = 1; o < 16; ++o) {
-    float2 v = __ldg(a.tw256 + ((q * o) & 255));
-    tw1[o - 1] = mk<float>(v.x, v.y);
+  // inter-pass twiddles live in shared tables (all lanes of a warp that share q read one address:
+  // broadcast), which frees the registers that carry the next block's samples across phases 2 and 3
+  for (int i = tid; i < 256; i += 16 * COLS) {
+    const float2 v = __ldg(a.tw256 + (((i >> 4) * (i & 15)) & 255));
+    t1s[i] = mk<float>(v.x, v.y);
   }
-#pragma unroll
-  for (int m = 1; m < 12; ++m) {
-    float2 v = __ldg(a.tw192 + ((q * m) % 192));
-    tw2[m - 1] = mk<float>(v.x, v.y);
+  for (int i = tid; i < 192; i += 16 * COLS) {
+    const float2 v = __ldg(a.tw192 + (((i >> 4) * (i & 15)) % 192));
+    t2s[i] = mk<float>(v.x, v.y);
   }
   __syncthreads();
 
@@ -562,18 +565,28 @@ __global__ void __launch_bounds__(16 * COLS, 512 / (16 * COLS)) pfb_resample_low
   C* eA = exA + c * kColStride;
   C* eB = exB + c * kColStride;
 
+  C xn[16];                                           // samples of the next block, in flight during phases 2-3
+  if (n_begin < n_end) {
+    const C* p = vcol + ((long long)n_begin * keep + q) * rowlen;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) xn[i] = ld_nc(p + i * 16 * rowlen);
+  }
   for (int n = n_begin; n < n_end; ++n) {
     C x[16];
     {
       // phase 1: lane q holds tau = q + 16 i
-      const C* p = vcol + ((long long)n * keep + q) * rowlen;
 #pragma unroll
-      for (int i = 0; i < 16; ++i) x[i] = ld_nc(p + i * 16 * rowlen) * stp[q + 16 * i];
+      for (int i = 0; i < 16; ++i) x[i] = xn[i] * stp[q + 16 * i];
+      if (n + 1 < n_end) {
+        const C* p = vcol + ((long long)(n + 1) * keep + q) * rowlen;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) xn[i] = ld_nc(p + i * 16 * rowlen);
+      }
       fft_reg<4, 4, -1>(x);
 #pragma unroll
       for (int o = 0; o < 16; ++o) {
         C v = x[slot<4, 4>(o)];
-        if (o) v = v * tw1[o - 1];
+        if (o) v = v * t1s[o * 16 + q];
         eA[o * kQStride + q] = v;
       }
     }
@@ -597,7 +610,7 @@ __global__ void __launch_bounds__(16 * COLS, 512 / (16 * COLS)) pfb_resample_low
 #pragma unroll
       for (int m = 0; m < 12; ++m) {
         C v = z[slot<3, 4>(m)];
-        if (m) v = v * tw2[m - 1];                        // exp(+2 pi i o m / 192)
+        if (m) v = v * t2s[m * 16 + o];                   // exp(+2 pi i o m / 192)
         eB[m * kQStride + o] = v;
       }
     }
@@ -616,148 +629,6 @@ __global__ void __launch_bounds__(16 * COLS, 512 / (16 * COLS)) pfb_resample_low
         const bool keep_j = (OV2 >= 0 && OV2 % 12 == 0) ? (12 * j >= OV2 && 12 * j < 192 - OV2)
                                                         : (m + 12 * j >= ov2 && m + 12 * j < 192 - ov2);
         if (keep_j) {
-          C v = x[slot<4, 4>(j)];
-          if (odd) v = mk<float>(-v.x, -v.y);
-          p[12 * j * rowlen] = v;
-        }
-      }
-    }
-  }
-}
-
-// ---------------------------------------------------------------------------
-// K3 v2: the same mathematics with (a) the fine-time rows of the CTA's 8 columns kept in a
-// shared-memory ring filled by cp.async one overlap-save block ahead (each row is fetched once:
-// no 1.6x overlap re-read, no exposed L2 latency), and (b) the 16 lanes of a column inside one
-// warp, so the three passes exchange data through a per-warp buffer with __syncwarp() only; the
-// single __syncthreads() per block publishes the prefetched rows.
-// ---------------------------------------------------------------------------
-constexpr int kRingRows = 416;                    // 256 (current block) + 160 (next block's new rows)
-constexpr int kRingPitch = 9;                     // 8 columns + 1: conflict-free column reads
-template <int NPOL> constexpr size_t res2_smem_bytes() {
-  return (size_t)kRingRows * kRingPitch * sizeof(C) + (size_t)4 * 2 * kColStride * sizeof(C) + 256 * sizeof(float);
-}
-
-__device__ __forceinline__ void cp_async8(void* dst, const void* src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
-}
-
-template <int NPOL, int NCHAN, bool FLIP>
-__global__ void __launch_bounds__(128, 4) pfb_resample_low2(const ResArgs a) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  C* ring = reinterpret_cast<C*>(smem_raw);                              // [416][9]
-  C* exw = ring + kRingRows * kRingPitch;                                // [4 warps][2 cols][273]
-  float* stp = reinterpret_cast<float*>(exw + 4 * 2 * kColStride);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int q = lane & 15, c = warp * 2 + (lane >> 4);                   // lane-in-transform, column 0..7
-  constexpr int T1G = 8 / NPOL;
-  const int nchan = NCHAN > 0 ? NCHAN : a.nchan;
-  const int rowlen = nchan * NPOL;
-  const int groups = nchan / T1G;
-  const int g = blockIdx.x % groups, sp = blockIdx.x / groups;
-  const int t1_0 = g * T1G, t1 = t1_0 + c / NPOL;
-  const int per = (a.nblk + a.nsplit - 1) / a.nsplit;
-  const int n_begin = sp * per, n_end = min(a.nblk, n_begin + per);
-  if (n_begin >= n_end) return;
-  const int keep = a.keep, keep2 = a.keep2, ov2 = a.ov2;                 // keep <= 160 is required by the ring size
-
-  stp[tid] = a.taper[tid];
-  stp[tid + 128] = a.taper[tid + 128];
-  C tw1[15], tw2[11];
-#pragma unroll
-  for (int o = 1; o < 16; ++o) {
-    float2 v = __ldg(a.tw256 + ((q * o) & 255));
-    tw1[o - 1] = mk<float>(v.x, v.y);
-  }
-#pragma unroll
-  for (int m = 1; m < 12; ++m) {
-    float2 v = __ldg(a.tw192 + ((q * m) % 192));
-    tw2[m - 1] = mk<float>(v.x, v.y);
-  }
-  const C* vbase = a.v + (long long)t1_0 * NPOL;
-  // copy `nrows` fine-time rows starting at row r0 (ring slot s0) of the CTA's 8 columns into the ring;
-  // thread t moves column t & 7 of rows (t >> 3) + 16 k
-  auto fetch = [&](long long r0, int s0, int nrows) {
-    const int cc = tid & 7;
-    const C* src = vbase + (r0 + (tid >> 3)) * rowlen + cc;
-    int slot = s0 + (tid >> 3);
-    for (int k = tid >> 3; k < nrows; k += 16) {
-      if (slot >= kRingRows) slot -= kRingRows;
-      cp_async8(ring + slot * kRingPitch + cc, src);
-      src += 16 * rowlen;
-      slot += 16;
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-  };
-  const long long row0 = (long long)n_begin * keep;
-  int slot_cur = 0;                                // ring slot of the current block's first row
-  fetch(row0, 0, 256);
-  C* e = exw + (size_t)(warp * 2 + (lane >> 4)) * kColStride;
-  const C* wcol = a.wt + (size_t)t1 * 192;
-  C* ocol = a.out + (long long)t1_0 * NPOL + c;
-
-  for (int n = n_begin; n < n_end; ++n) {
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    __syncthreads();                               // block n's rows are in the ring; block n-1 fully consumed
-    if (n + 1 < n_end) {
-      int s_new = slot_cur + 256;
-      if (s_new >= kRingRows) s_new -= kRingRows;
-      fetch((long long)n * keep + 256, s_new, keep);
-    }
-    C x[16];
-    {
-      const int base = slot_cur + q;
-      slot_cur += keep;
-      if (slot_cur >= kRingRows) slot_cur -= kRingRows;
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        int r = base + 16 * i;
-        if (r >= kRingRows) r -= kRingRows;
-        x[i] = ring[r * kRingPitch + c] * stp[q + 16 * i];
-      }
-      fft_reg<4, 4, -1>(x);
-      __syncwarp();                                // previous block's phase-3 reads of e are done
-#pragma unroll
-      for (int o = 0; o < 16; ++o) {
-        C v = x[slot<4, 4>(o)];
-        if (o) v = v * tw1[o - 1];
-        e[o * kQStride + q] = v;
-      }
-    }
-    __syncwarp();
-    {
-      const int o = q;
-#pragma unroll
-      for (int i = 0; i < 16; ++i) x[i] = e[o * kQStride + i];
-      fft_reg<4, 4, -1>(x);
-      C z[12];
-#pragma unroll
-      for (int k = 0; k < 12; ++k) {
-        const int o2 = k < 6 ? k : k + 4;
-        const int b = o + 16 * o2;
-        const int rr = b < 96 ? b + 96 : b - 160;
-        z[k] = x[slot<4, 4>(o2)] * ld_nc(wcol + rr);
-      }
-      fft_reg<3, 4, +1>(z);
-      __syncwarp();                                // everyone has read its phase-2 inputs
-#pragma unroll
-      for (int m = 0; m < 12; ++m) {
-        C v = z[slot<3, 4>(m)];
-        if (m) v = v * tw2[m - 1];
-        e[m * kQStride + o] = v;
-      }
-    }
-    __syncwarp();
-    if (q < 12) {
-      const int m = q;
-#pragma unroll
-      for (int i = 0; i < 16; ++i) x[i] = e[m * kQStride + i];
-      fft_reg<4, 4, +1>(x);
-      C* p = ocol + ((long long)n * keep2 - ov2 + m) * rowlen;
-      const bool odd = FLIP && (m & 1);
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        if (m + 12 * j >= ov2 && m + 12 * j < 192 - ov2) {
           C v = x[slot<4, 4>(j)];
           if (odd) v = mk<float>(-v.x, -v.y);
           p[12 * j * rowlen] = v;
@@ -1000,11 +871,6 @@ inline long long low_resample_nsplit(const void* d_low, int npol) {
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  if (getenv("PFB_RESAMPLE_V2")) {                    // experimental ring variant: 8 columns, 4 CTAs per SM
-    const int groups2 = h->nchan / (8 / npol);
-    long long n2 = ((long long)sms * 4) / groups2;
-    return n2 < 1 ? 1 : n2;
-  }
   const int groups = h->nchan / (16 / npol);         // 16 columns per CTA, 2 CTAs per SM
   long long n = ((long long)sms * 2) / groups;
   return n < 1 ? 1 : n;
@@ -1038,34 +904,6 @@ inline int low_resample_launch<float>(const void* d_low, const void* v, void* ou
   a.nsplit = (int)nsplit;
   const long long grid = nsplit * groups;
   cudaError_t e = cudaSuccess;
-  if (h->keep <= 160 && h->keep >= 96 && getenv("PFB_RESAMPLE_V2")) {
-    // v2: 8 columns / 128 threads per CTA, 4 CTAs per SM
-    const int groups2 = h->nchan / (8 / npol);
-    long long ns = ((long long)sms * 4) / groups2;
-    if (ns > nblk) ns = nblk;
-    if (ns < 1) ns = 1;
-    a.nsplit = (int)ns;
-    const long long grid2 = ns * groups2;
-    auto go2 = [&](auto kernel, size_t smem) {
-      e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e != cudaSuccess) return;
-      kernel<<<(unsigned)grid2, 128, smem, st>>>(a);
-    };
-    if (npol == 2) {
-      if (h->nchan == 256 && !h->flip) go2(low::pfb_resample_low2<2, 256, false>, low::res2_smem_bytes<2>());
-      else if (h->flip) go2(low::pfb_resample_low2<2, 0, true>, low::res2_smem_bytes<2>());
-      else go2(low::pfb_resample_low2<2, 0, false>, low::res2_smem_bytes<2>());
-    } else {
-      if (h->nchan == 256 && !h->flip) go2(low::pfb_resample_low2<1, 256, false>, low::res2_smem_bytes<1>());
-      else if (h->flip) go2(low::pfb_resample_low2<1, 0, true>, low::res2_smem_bytes<1>());
-      else go2(low::pfb_resample_low2<1, 0, false>, low::res2_smem_bytes<1>());
-    }
-    if (e != cudaSuccess) return (int)e;
-    e = cudaGetLastError();
-    if (e != cudaSuccess) return (int)e;
-    *done = true;
-    return 0;
-  }
   constexpr int COLS = 16;
   {
     const int groupsv = h->nchan / (COLS / npol);
