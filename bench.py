@@ -304,9 +304,7 @@ def run_b200(args):
     start.record()
     for i in range(K):
         ev[i][0].record()
-        from ska_pst_dsp_model_b200.sharding import exchange_halo
-        exchange_halo(torch.view_as_real(rt.local), shard)
-        rt.analysis.segment(rt.local, shard.own0, shard.fine0, shard.fine_n, out=rt.chan)
+        rt.run_analysis()
         ev[i][1].record()
         rt.inverse(rt.chan, out=rt.out)
         ev[i][2].record()

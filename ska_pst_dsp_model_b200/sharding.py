@@ -87,20 +87,25 @@ def plan_time_shards(n_dat, world, nchan, os_factor, ntaps, input_fft_length, in
     return out
 
 
-def exchange_halo(local, shard: TimeShard, group=None):
-    """Fill ``local[own_n : own_n + halo_n]`` with the first samples of rank+1.
+def start_halo_exchange(local, shard: TimeShard, group=None):
+    """Enqueue the neighbour transfer that fills ``local[own_n : own_n + halo_n]`` with the first
+    samples of rank+1; returns the request handles (wait on them before touching the halo).
 
     ``local``: real-valued view ``[own_n + halo_n, npol, 2]`` (torch.view_as_real
     of the complex shard) on the device the process group communicates on."""
     import torch.distributed as dist
     if shard.world == 1:
-        return
+        return []
     ops = []
     if shard.send_n > 0:
         ops.append(dist.P2POp(dist.isend, local[: shard.send_n], shard.rank - 1, group))
     if shard.halo_n > 0:
         ops.append(dist.P2POp(dist.irecv, local[shard.own_n: shard.own_n + shard.halo_n], shard.rank + 1, group))
-    for req in dist.batch_isend_irecv(ops):
+    return dist.batch_isend_irecv(ops)
+
+
+def exchange_halo(local, shard: TimeShard, group=None):
+    for req in start_halo_exchange(local, shard, group):
         req.wait()
 
 
@@ -126,8 +131,24 @@ class ShardedRoundTrip:
         self.local[: self.shard.own_n].copy_(x_owned)
 
     def step(self, group=None):
-        s = self.shard
-        exchange_halo(self.torch.view_as_real(self.local), s, group)
-        self.analysis.segment(self.local, s.own0, s.fine0, s.fine_n, out=self.chan)
+        self.run_analysis(group)
         self.inverse(self.chan, out=self.out)
         return self.out
+
+    def run_analysis(self, group=None):
+        """Halo exchange overlapped with the analysis of the interior blocks (those whose FIR window
+        lies inside the owned samples), then the few tail blocks, then the inversion."""
+        s = self.shard
+        reqs = start_halo_exchange(self.torch.view_as_real(self.local), s, group)
+        if not reqs:
+            self.analysis.segment(self.local, s.own0, s.fine0, s.fine_n, out=self.chan)
+        else:
+            a = self.analysis
+            k_int = max(0, (s.own_n - a.fl) // a.step + 1)
+            k_int = min(s.fine_n, k_int // 4 * 4)          # multiple of nu: the tail launch starts rotation-free
+            if k_int > 0:
+                a.segment(self.local[: s.own_n], s.own0, s.fine0, k_int, out=self.chan[:k_int])
+            for r in reqs:
+                r.wait()
+            if k_int < s.fine_n:
+                a.segment(self.local, s.own0, s.fine0 + k_int, s.fine_n - k_int, out=self.chan[k_int:])
