@@ -306,8 +306,10 @@ template <typename T> static int analysis_launch(pfb_analysis_plan* p, AnalysisA
 static int analysis_run(pfb_analysis_plan* p, const void* in, long long n_local, long long sample0, void* out,
                         int npol, long long k_first, long long nblk, long long kout0, long long kout_mod,
                         int first_call, void* stream) {
-  if (!p || !in || !out) return fail(PFB_ERR_ARG, "null pointer");
+  if (!p) return fail(PFB_ERR_ARG, "null plan");
   if (npol < 1 || npol > 2) return fail(PFB_ERR_ARG, "npol must be 1 or 2");
+  if (nblk <= 0) return PFB_OK;                      // nothing to do (empty / too short input)
+  if (!in || !out) return fail(PFB_ERR_ARG, "null pointer");
   CU(cudaSetDevice(p->device));
   AnalysisArgs a;
   memset(&a, 0, sizeof(a));
@@ -704,8 +706,10 @@ int pfb_inverse_get_profile(pfb_inverse_plan* p, double* ms, long long* launches
 
 int pfb_inverse_execute(pfb_inverse_plan* p, const void* in_dev, void* out_dev, int npol, long long n_dat,
                         void* stream) {
-  if (!p || !in_dev || !out_dev) return fail(PFB_ERR_ARG, "null pointer");
+  if (!p) return fail(PFB_ERR_ARG, "null plan");
   if (npol < 1 || npol > 2) return fail(PFB_ERR_ARG, "npol must be 1 or 2");
+  if (pfb_inverse_nblocks(p, n_dat) <= 0) return PFB_OK;     // nothing to do
+  if (!in_dev || !out_dev) return fail(PFB_ERR_ARG, "null pointer");
   CU(cudaSetDevice(p->device));
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (p->spectral)
