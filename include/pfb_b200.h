@@ -59,6 +59,11 @@ int pfb_analysis_nchan_out(const pfb_analysis_plan* plan); /* block, or 216 for 
 /* in: [n_dat][npol]; out: [nblocks][nchan_out][npol] */
 int pfb_analysis_execute(pfb_analysis_plan* plan, const void* in_dev, void* out_dev, int npol,
                          long long n_dat, int first_call, void* stream);
+/* Batched form (TwoStageFilterBank.m:92-96: one stage-2 filterbank per coarse channel, here one launch):
+ * in: [n_dat][nstreams] independent single-pol streams; out_layout 0: [nblocks][nchan_out][nstreams],
+ * 1: [nblocks][nstreams][nchan_out] (coarse-major, the channel order TwoStageFilterBank produces). */
+int pfb_analysis_execute_batched(pfb_analysis_plan* plan, const void* in_dev, void* out_dev, int nstreams,
+                                 long long n_dat, int first_call, int out_layout, void* stream);
 /* Time-segment form (multi-GPU sharding / streaming, cf. FilterBank.m:85-88,119-126):
  * compute output blocks [k_first, k_first+nblk) of the stream. in_dev[0] is absolute
  * stream sample `sample0`, n_local samples are resident; samples outside read as 0.
@@ -84,6 +89,11 @@ long long pfb_inverse_out_len(const pfb_inverse_plan* plan, long long n_dat); /*
 /* in: [n_dat][nchan][npol]; out: [out_len][npol] */
 int pfb_inverse_execute(pfb_inverse_plan* plan, const void* in_dev, void* out_dev, int npol,
                         long long n_dat, void* stream);
+/* Batched form (TwoStageInverseFilterBank.m:117-151: one inversion per output coarse channel):
+ * in: [n_dat][ngroups][nchan][npol]; out: [nblocks*keep2][ngroups][nchan][npol] where keep2 =
+ * FN_width - 2*overlap*de/nu; output sample T2*nchan + t1 of group g is element [T2][g][t1]. */
+int pfb_inverse_execute_batched(pfb_inverse_plan* plan, const void* in_dev, void* out_dev, int ngroups,
+                                int npol, long long n_dat, void* stream);
 /* spectral (frequency-domain) taper of polyphase_synthesis.m:282 / InverseFilterBank.frequency_taper:
  * n = nchan*FN_width doubles multiplying the stitched spectrum (NULL clears it).  With a taper set
  * the inversion runs the literal-order chain (per-channel FFT -> weights -> channel IDFT -> bin IFFT). */

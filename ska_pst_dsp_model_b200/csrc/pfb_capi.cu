@@ -267,11 +267,24 @@ long long pfb_analysis_nblocks(const pfb_analysis_plan* p, long long n_dat, int 
 
 int pfb_analysis_nchan_out(const pfb_analysis_plan* p) { return p ? p->nchan_out : PFB_ERR_ARG; }
 
-template <typename T> static int analysis_launch_generic(AnalysisArgs a, long long b0, long long b1, cudaStream_t st) {
+template <typename T> static int analysis_launch_generic(AnalysisArgs a, long long b0, long long b1, cudaStream_t st,
+                                                          int nstreams = 0) {
   if (b1 <= b0) return PFB_OK;
   a.start0 += b0 * (long long)a.S;
   a.kout0 += b0;
   a.nblocks = b1 - b0;
+  unsigned gy = 1;
+  if (nstreams > 0) {               // batched: tile the streams over blockIdx.y
+    int tile = 16;
+    while (tile > 1 && (nstreams % tile || (size_t)tile * padded_len<T>(a.N) * sizeof(Cx<T>) > 96 * 1024)) tile /= 2;
+    a.npol = tile;
+    gy = (unsigned)(nstreams / tile);
+  } else {
+    a.in_pitch = a.npol;
+    a.out_sk = (long long)a.nchan_out * a.npol;
+    a.out_sc = a.npol;
+    a.out_sp = 1;
+  }
   const int ld = padded_len<T>(a.N);
   int kb = 4096 / (a.N * a.npol);
   if (kb < 1) kb = 1;
@@ -280,8 +293,8 @@ template <typename T> static int analysis_launch_generic(AnalysisArgs a, long lo
   int rc = set_smem(pfb_analysis_generic<T>, smem);
   if (rc) return rc;
   const long long grid = (a.nblocks + kb - 1) / kb;
-  if (grid > 2147483647ll) return fail(PFB_ERR_ARG, "too many blocks for one launch");
-  pfb_analysis_generic<T><<<(unsigned)grid, 256, smem, st>>>(a);
+  if (grid > 2147483647ll || gy > 65535u) return fail(PFB_ERR_ARG, "too many blocks for one launch");
+  pfb_analysis_generic<T><<<dim3((unsigned)grid, gy), 256, smem, st>>>(a);
   return check_launch("pfb_analysis_generic");
 }
 
@@ -337,6 +350,32 @@ int pfb_analysis_execute(pfb_analysis_plan* plan, const void* in_dev, void* out_
     kout0 = (nb - (plan->sds % nb)) % nb;
   }
   return analysis_run(plan, in_dev, n_dat, 0, out_dev, npol, 0, nb, kout0, kmod, first_call, stream);
+}
+
+int pfb_analysis_execute_batched(pfb_analysis_plan* p, const void* in_dev, void* out_dev, int nstreams, long long n_dat,
+                                 int first_call, int out_layout, void* stream) {
+  if (!p) return fail(PFB_ERR_ARG, "null plan");
+  if (nstreams < 1 || (out_layout != 0 && out_layout != 1)) return fail(PFB_ERR_ARG, "pfb_analysis_execute_batched: bad argument");
+  const long long nb = pfb_analysis_nblocks(p, n_dat, first_call);
+  if (nb <= 0) return PFB_OK;
+  if (!in_dev || !out_dev) return fail(PFB_ERR_ARG, "null pointer");
+  CU(cudaSetDevice(p->device));
+  AnalysisArgs a;
+  memset(&a, 0, sizeof(a));
+  a.in = in_dev; a.out = out_dev; a.taps = p->d_taps; a.fft = p->fft;
+  a.N = p->N; a.S = p->S; a.P = p->P; a.n_dat = n_dat;
+  long long start_abs0 = 0, rot = 0;
+  if (p->variant == PFB_VARIANT_PADDED) { start_abs0 = -(long long)p->fl; rot = 1; }
+  if (p->variant == PFB_VARIANT_LOWCBF) { start_abs0 = first_call ? -1536 : 0; rot = first_call ? 1536 : 0; }
+  a.start0 = start_abs0; a.phase0 = rot; a.nblocks = nb;
+  if (p->variant == PFB_VARIANT_PADDED) { a.kout_mod = nb; a.kout0 = (nb - (p->sds % nb)) % nb; }
+  a.chan_first = p->chan_first; a.nchan_out = p->nchan_out; a.scale = p->scale;
+  a.in_pitch = nstreams;
+  if (out_layout == 0) { a.out_sk = (long long)p->nchan_out * nstreams; a.out_sc = nstreams; a.out_sp = 1; }       // [k][chan][stream]
+  else { a.out_sk = (long long)p->nchan_out * nstreams; a.out_sc = 1; a.out_sp = p->nchan_out; }                    // [k][stream][chan]
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  return p->dtype == PFB_DTYPE_C64 ? analysis_launch_generic<float>(a, 0, nb, st, nstreams)
+                                   : analysis_launch_generic<double>(a, 0, nb, st, nstreams);
 }
 
 int pfb_analysis_execute_segment(pfb_analysis_plan* plan, const void* in_dev, long long n_local, long long sample0,
@@ -501,28 +540,30 @@ static int launch_chan_idft(pfb_inverse_plan* p, const void* in, void* out, int 
 }
 
 template <typename T>
-static int launch_resample(pfb_inverse_plan* p, const void* v, void* out, int npol, long long nblk, cudaStream_t st) {
+static int launch_resample(pfb_inverse_plan* p, const void* v, void* out, int npol, long long nblk, cudaStream_t st,
+                           int G = 1) {
   if (nblk <= 0) return PFB_OK;
   const int tok = p->prof_begin(1, st);
   if (p->low_fast) {
     bool done = false;
-    int rc = low_resample_launch<T>(p->d_low, v, out, npol, nblk, st, &done);
+    int rc = low_resample_launch<T>(p->d_low, v, out, npol, nblk, G, st, &done);
     if (rc) return fail(PFB_ERR_CUDA, "pfb_resample_low launch: %s", cudaGetErrorString((cudaError_t)rc));
     if (done) { p->prof_end(tok, st); return check_launch("pfb_resample_low"); }
   }
   ResampleArgs a;
   memset(&a, 0, sizeof(a));
   a.v = v; a.out = out; a.fwd = p->fft_fwd; a.bwd = p->fft_bwd; a.taper = p->d_taper; a.wt = p->d_wt;
-  a.nchan = p->nchan; a.npol = npol; a.Nf = p->Nf; a.FNw = p->FNw; a.keep = p->keep; a.ov2 = p->ov2;
+  const int nchan_total = p->nchan * G;
+  a.nchan = nchan_total; a.wt_mod = p->nchan; a.npol = npol; a.Nf = p->Nf; a.FNw = p->FNw; a.keep = p->keep; a.ov2 = p->ov2;
   a.keep2 = p->keep2; a.off = p->off; a.d2 = p->d2;
   const size_t percol = (size_t)(padded_len<T>(p->Nf) + padded_len<T>(p->FNw)) * sizeof(Cx<T>);
   int tg = 1;
-  while (p->nchan % (tg * 2) == 0 && (size_t)(tg * 2) * npol * percol <= 110 * 1024) tg *= 2;
+  while (nchan_total % (tg * 2) == 0 && (size_t)(tg * 2) * npol * percol <= 110 * 1024) tg *= 2;
   a.tg = tg;
   const size_t smem = (size_t)tg * npol * percol;
   int rc = set_smem(pfb_resample_generic<T>, smem);
   if (rc) return rc;
-  const long long groups = p->nchan / tg;
+  const long long groups = nchan_total / tg;
   // keep each launch's grid within 2^31 and the block count in an int
   long long done = 0;
   while (done < nblk) {
@@ -530,7 +571,7 @@ static int launch_resample(pfb_inverse_plan* p, const void* v, void* out, int np
     const long long maxb = 2000000000ll / groups;
     if (nb > maxb) nb = maxb;
     a.nblk = (int)nb;
-    const long long rowlen = (long long)p->nchan * npol;
+    const long long rowlen = (long long)nchan_total * npol;
     a.v = reinterpret_cast<const Cx<T>*>(v) + done * p->keep * rowlen;
     a.out = reinterpret_cast<Cx<T>*>(out) + done * p->keep2 * rowlen;
     pfb_resample_generic<T><<<(unsigned)(nb * groups), 256, smem, st>>>(a);
@@ -543,14 +584,15 @@ static int launch_resample(pfb_inverse_plan* p, const void* v, void* out, int np
 }
 
 template <typename T>
-static int inverse_run(pfb_inverse_plan* p, const void* in, void* out, int npol, long long n_dat, cudaStream_t st) {
+static int inverse_run(pfb_inverse_plan* p, const void* in, void* out, int npol, long long n_dat, cudaStream_t st,
+                       int G = 1) {
   const long long nblocks = pfb_inverse_nblocks(p, n_dat);
   if (nblocks <= 0) return PFB_OK;
-  const long long rowbytes = (long long)p->nchan * npol * sizeof(Cx<T>);
+  const long long rowbytes = (long long)p->nchan * G * npol * sizeof(Cx<T>);
   long long B = (p->scratch_bytes - (long long)2 * p->ov * rowbytes) / ((long long)p->keep * rowbytes);
   if (B < 1) B = 1;
   if (p->low_fast) {                    // equal work per CTA of the one-wave resample grid
-    const long long ns = low_resample_nsplit(p->d_low, npol);
+    const long long ns = low_resample_nsplit(p->d_low, npol, G);
     if (B >= ns) B = B / ns * ns;
   }
   if (B > nblocks) B = nblocks;
@@ -561,15 +603,15 @@ static int inverse_run(pfb_inverse_plan* p, const void* in, void* out, int npol,
     CU(cudaMalloc(&p->d_scratch, need));
     p->scratch_cap = need;
   }
-  const long long rowlen = (long long)p->nchan * npol;
+  const long long rowlen = (long long)p->nchan * G * npol;
   for (long long n0 = 0; n0 < nblocks; n0 += B) {
     const long long nb = (nblocks - n0 < B) ? nblocks - n0 : B;
     const long long rows = (nb - 1) * p->keep + p->Nf;
     const Cx<T>* src = reinterpret_cast<const Cx<T>*>(in) + n0 * p->keep * rowlen;
-    int rc = launch_chan_idft<T>(p, src, p->d_scratch, npol, rows, st);
+    int rc = launch_chan_idft<T>(p, src, p->d_scratch, npol, rows * G, st);      // every (tau, group) is one row
     if (rc) return rc;
     Cx<T>* dst = reinterpret_cast<Cx<T>*>(out) + n0 * p->keep2 * rowlen;
-    rc = launch_resample<T>(p, p->d_scratch, dst, npol, nb, st);
+    rc = launch_resample<T>(p, p->d_scratch, dst, npol, nb, st, G);
     if (rc) return rc;
   }
   return PFB_OK;
@@ -717,6 +759,19 @@ int pfb_inverse_execute(pfb_inverse_plan* p, const void* in_dev, void* out_dev, 
                                      : inverse_run_literal<double>(p, in_dev, out_dev, npol, n_dat, st);
   return p->dtype == PFB_DTYPE_C64 ? inverse_run<float>(p, in_dev, out_dev, npol, n_dat, st)
                                    : inverse_run<double>(p, in_dev, out_dev, npol, n_dat, st);
+}
+
+int pfb_inverse_execute_batched(pfb_inverse_plan* p, const void* in_dev, void* out_dev, int ngroups, int npol,
+                                long long n_dat, void* stream) {
+  if (!p) return fail(PFB_ERR_ARG, "null plan");
+  if (npol < 1 || npol > 2 || ngroups < 1) return fail(PFB_ERR_ARG, "pfb_inverse_execute_batched: bad argument");
+  if (p->spectral) return fail(PFB_ERR_UNSUPPORTED, "batched inversion with a spectral taper is not implemented");
+  if (pfb_inverse_nblocks(p, n_dat) <= 0) return PFB_OK;
+  if (!in_dev || !out_dev) return fail(PFB_ERR_ARG, "null pointer");
+  CU(cudaSetDevice(p->device));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  return p->dtype == PFB_DTYPE_C64 ? inverse_run<float>(p, in_dev, out_dev, npol, n_dat, st, ngroups)
+                                   : inverse_run<double>(p, in_dev, out_dev, npol, n_dat, st, ngroups);
 }
 
 int pfb_inverse_execute_stage(pfb_inverse_plan* p, int stage, const void* in_dev, void* out_dev, int npol,

@@ -30,6 +30,9 @@ struct AnalysisArgs {
   int nchan_out;
   double scale;
   int kb;                // blocks per CTA
+  // batched form: `in` holds in_pitch independent streams per time sample; blockIdx.y selects a tile of
+  // npol of them; output element (k, chan, stream) lives at k*out_sk + chan*out_sc + stream*out_sp
+  long long in_pitch, out_sk, out_sc, out_sp;
 };
 
 template <typename T>
@@ -39,7 +42,8 @@ __global__ void __launch_bounds__(256) pfb_analysis_generic(const AnalysisArgs a
   const int N = a.N, npol = a.npol, ld = padded_len<T>(N);
   const long long k0 = (long long)blockIdx.x * a.kb;
   const int kb = (int)min((long long)a.kb, a.nblocks - k0);
-  const Cx<T>* __restrict__ x = reinterpret_cast<const Cx<T>*>(a.in);
+  const int pol0 = blockIdx.y * npol;
+  const Cx<T>* __restrict__ x = reinterpret_cast<const Cx<T>*>(a.in) + pol0;
   const T* __restrict__ f = reinterpret_cast<const T*>(a.taps);
 
   // FIR: work item = (kk, j, pol), pol fastest -> coalesced over [t][pol]
@@ -53,7 +57,7 @@ __global__ void __launch_bounds__(256) pfb_analysis_generic(const AnalysisArgs a
     for (int m = 0; m < a.P; ++m) {
       const long long t = t0 + j + (long long)m * N;
       if (t >= 0 && t < a.n_dat) {
-        const Cx<T> v = ldg_cx<T>(x + t * npol + pol);
+        const Cx<T> v = ldg_cx<T>(x + t * a.in_pitch + pol);
         const T c = __ldg(f + j + m * N);
         accx += c * v.x;
         accy += c * v.y;
@@ -78,7 +82,7 @@ __global__ void __launch_bounds__(256) pfb_analysis_generic(const AnalysisArgs a
     const Cx<T> v = s[(size_t)(kk * npol + pol) * ld + padi<T>(__ldg(a.fft.perm + c))];
     long long ko = k0 + kk + a.kout0;
     if (a.kout_mod > 0) ko %= a.kout_mod;
-    out[(ko * nco + ci) * npol + pol] = v * scale;
+    out[ko * a.out_sk + ci * a.out_sc + (pol0 + pol) * a.out_sp] = v * scale;
   }
 }
 
@@ -144,6 +148,7 @@ struct ResampleArgs {
   int nchan, npol, Nf, FNw, keep, ov2, keep2, off, d2;
   int tg;               // t1 values per CTA
   int nblk;             // overlap-save blocks in this launch
+  int wt_mod;           // channels per group: column t1 uses weight row t1 % wt_mod (batched groups)
 };
 
 template <typename T>
@@ -172,7 +177,7 @@ __global__ void __launch_bounds__(256) pfb_resample_generic(const ResampleArgs a
   const Cx<T>* __restrict__ wt = reinterpret_cast<const Cx<T>*>(a.wt);
   for (int e = threadIdx.x; e < a.FNw * ncol; e += blockDim.x) {
     const int r = e % a.FNw, col = e / a.FNw;
-    const int t1 = t1_0 + col / a.npol;
+    const int t1 = (t1_0 + col / a.npol) % a.wt_mod;
     int b = r + a.d2 + a.Nf / 2;
     if (b >= a.Nf) b -= a.Nf;
     int rp = r - a.off;

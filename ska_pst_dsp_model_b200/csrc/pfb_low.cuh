@@ -510,6 +510,7 @@ struct ResArgs {
   int nchan, keep, ov2, keep2, flip;   // flip: critical sampling => y *= (-1)^t2
   int nblk;             // overlap-save blocks in this launch
   int nsplit;           // CTAs per column group along n
+  int wt_mod;           // channels per group (weight row = t1 % wt_mod)
 };
 
 template <int COLS> constexpr size_t res_smem_bytes() {
@@ -545,7 +546,7 @@ __global__ void __launch_bounds__(16 * COLS, 512 / (16 * COLS)) pfb_resample_low
 
   for (int i = tid; i < COLS * 192; i += 16 * COLS) {
     const int cc = i / 192, rr = i % 192;
-    swt[cc * 193 + rr] = a.wt[(size_t)(t1_0 + cc / NPOL) * 192 + rr];
+    swt[cc * 193 + rr] = a.wt[(size_t)((t1_0 + cc / NPOL) % a.wt_mod) * 192 + rr];
   }
   for (int i = tid; i < 256; i += 16 * COLS) stp[i] = a.taper[i];
   // inter-pass twiddles live in shared tables (all lanes of a warp that share q read one address:
@@ -866,25 +867,25 @@ inline int low_chan_idft_launch<float>(const void* d_low, const void* in, void* 
 }
 
 // preferred divisor of the chunk length (blocks) so every CTA of the resample wave gets equal work
-inline long long low_resample_nsplit(const void* d_low, int npol) {
+inline long long low_resample_nsplit(const void* d_low, int npol, int groups_b = 1) {
   const low::LowInverse* h = reinterpret_cast<const low::LowInverse*>(d_low);
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int groups = h->nchan / (16 / npol);         // 16 columns per CTA, 2 CTAs per SM
+  const int groups = h->nchan * groups_b / (16 / npol);   // 16 columns per CTA, 2 CTAs per SM
   long long n = ((long long)sms * 2) / groups;
   return n < 1 ? 1 : n;
 }
 
 template <typename T>
-int low_resample_launch(const void* d_low, const void* v, void* out, int npol, long long nblk, cudaStream_t st, bool* done) {
+int low_resample_launch(const void* d_low, const void* v, void* out, int npol, long long nblk, int groups_b, cudaStream_t st, bool* done) {
   *done = false;
   return 0;
 }
 
 template <>
 inline int low_resample_launch<float>(const void* d_low, const void* v, void* out, int npol, long long nblk,
-                                      cudaStream_t st, bool* done) {
+                                      int groups_b, cudaStream_t st, bool* done) {
   *done = false;
   const low::LowInverse* h = reinterpret_cast<const low::LowInverse*>(d_low);
   if (nblk > 2000000000ll) return 0;
@@ -892,9 +893,10 @@ inline int low_resample_launch<float>(const void* d_low, const void* v, void* ou
   a.v = reinterpret_cast<const low::C*>(v);
   a.out = reinterpret_cast<low::C*>(out);
   a.taper = h->taper; a.wt = h->wt; a.tw256 = h->tw256; a.tw192 = h->tw192;
-  a.nchan = h->nchan; a.keep = h->keep; a.ov2 = h->ov2; a.keep2 = h->keep2; a.flip = h->flip;
+  const int nchan_total = h->nchan * groups_b;        // batched groups are extra columns
+  a.nchan = nchan_total; a.wt_mod = h->nchan; a.keep = h->keep; a.ov2 = h->ov2; a.keep2 = h->keep2; a.flip = h->flip;
   a.nblk = (int)nblk;
-  const int groups = h->nchan / (16 / npol);
+  const int groups = nchan_total / (16 / npol);
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -906,19 +908,19 @@ inline int low_resample_launch<float>(const void* d_low, const void* v, void* ou
   cudaError_t e = cudaSuccess;
   constexpr int COLS = 16;
   {
-    const int groupsv = h->nchan / (COLS / npol);
+    const int groupsv = nchan_total / (COLS / npol);
     long long ns = ((long long)sms * (512 / (16 * COLS))) / groupsv;
     if (ns > nblk) ns = nblk;
     if (ns < 1) ns = 1;
     a.nsplit = (int)ns;
   }
-  const long long gridv = (long long)a.nsplit * (h->nchan / (COLS / npol));
+  const long long gridv = (long long)a.nsplit * (nchan_total / (COLS / npol));
   auto go = [&](auto kernel, size_t smem) {
     e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return;
     kernel<<<(unsigned)gridv, 16 * COLS, smem, st>>>(a);
   };
-  const bool low_shape = h->nchan == 256 && h->ov2 == 36;      // the SKA-Low PST configuration
+  const bool low_shape = nchan_total == 256 && h->ov2 == 36;   // the SKA-Low PST configuration
   if (npol == 2) {
     if (low_shape && !h->flip) go(low::pfb_resample_low<2, 256, 36, false, COLS>, low::res_smem_bytes<COLS>());
     else if (h->flip) go(low::pfb_resample_low<2, 0, -1, true, COLS>, low::res_smem_bytes<COLS>());

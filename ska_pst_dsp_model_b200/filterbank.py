@@ -139,46 +139,82 @@ class InverseFilterBank:
         return out
 
 
+class _BatchedFilterBank(FilterBank):
+    """FilterBank.m semantics applied to many single-pol streams at once (one tail buffer for all)."""
+
+    def execute_batched(self, x):
+        torch = _torch()
+        if self.rnd_input:
+            scale = 1.0
+            if self.rms_input > 0:
+                scale = self.rms_input / _std_all(x)
+            x = _matlab_round(scale * x)
+        if self.buffered_samples > 0:
+            x = torch.cat([self.input_buffer, x], dim=0)
+            self.buffered_samples = 0
+        x = x.contiguous()
+        n_in = x.shape[0]
+        out = self.plan.batched(x, first_call=self._first_call, coarse_major=True)     # [k2][stream][chan]
+        self._first_call = False
+        rem = out.shape[0] % self.os_factor.nu
+        if rem:
+            out = out[: out.shape[0] - rem]
+        if self.rnd_output:
+            # FilterBank.m:106-113 scales each stage-2 filterbank by its own output rms
+            if self.rms_output:
+                n = out.shape[0] * out.shape[2]
+                mean = out.mean(dim=(0, 2), keepdim=True)
+                std = torch.sqrt(((out - mean).abs() ** 2).sum(dim=(0, 2), keepdim=True) / (n - 1))
+                out = out * (self.rms_output / std)
+            out = _matlab_round(out)
+        input_idat = out.shape[0] * self.n_chan * self.os_factor.de // self.os_factor.nu
+        self.buffered_samples = n_in - input_idat
+        if self.buffered_samples > 0:
+            self.input_buffer = x[input_idat:].clone()
+        return out
+
+
 class TwoStageFilterBank:
-    """Stage 1 on polarisation 0 only, one stage-2 FilterBank per coarse channel (they share one
-    plan), optional critical chomp and single-channel output (TwoStageFilterBank.m:58-116)."""
+    """Stage 1 on polarisation 0 only, then one stage-2 filterbank per coarse channel - here a single
+    batched launch over all coarse channels - optional critical chomp and single-channel output
+    (TwoStageFilterBank.m:58-116)."""
 
     def __init__(self, cfg1: dict, cfg2: dict = None, critical=False, single=False):
         cfg2 = cfg2 or cfg1
         self.stage1 = FilterBank(**cfg1)
-        first = FilterBank(**cfg2)
-        self.stage2 = [first] + [FilterBank(**cfg2, plan=first.plan) for _ in range(self.stage1.n_chan - 1)]
+        self.stage2 = _BatchedFilterBank(**cfg2)
         self.critical, self.single = critical, single
 
     def execute(self, x):
         torch = _torch()
-        out1 = self.stage1.execute(x[:, 0:1].contiguous())            # :69 pol 1 only
+        out1 = self.stage1.execute(x[:, 0:1].contiguous())            # :69 pol 1 only -> [k1][nch1][1]
         os_ = self.stage1.os_factor
-        nch1 = self.stage1.n_chan
-        nch2_orig = self.stage2[0].n_chan
+        nch1 = 1 if self.single else self.stage1.n_chan
+        nch2_orig = self.stage2.n_chan
         nch2 = nch2_orig * os_.de // os_.nu if self.critical else nch2_orig
         offset = nch2_orig - nch2
-        if self.single:
-            nch1 = 1
-        out = None
+        tmp = self.stage2.execute_batched(out1[:, :nch1, 0].contiguous())   # [k2][nch1][nch2_orig]
         h = nch2 // 2
-        for ich in range(nch1):
-            tmp = self.stage2[ich].execute(out1[:, ich, 0:1].contiguous())
-            if out is None:
-                out = torch.zeros((tmp.shape[0], nch1 * nch2, 1), dtype=torch.complex64, device=tmp.device)   # :99 'single'
-            out[:, ich * nch2: ich * nch2 + h] = tmp[:, :h]                                                    # :104
-            out[:, ich * nch2 + h - 1: (ich + 1) * nch2] = tmp[:, h - 1 + offset: nch2 + offset]               # :105
-        return out
+        if offset:
+            # :104-105 - keep [0, h) and [h-1+offset, nch2+offset); the second assignment overwrites index h-1
+            idx = torch.cat([torch.arange(0, h - 1, device=tmp.device),
+                             torch.arange(h - 1 + offset, nch2 + offset, device=tmp.device)])
+            tmp = tmp.index_select(2, idx)
+        out = tmp.reshape(tmp.shape[0], nch1 * nch2, 1).to(torch.complex64)   # :99 'single'
+        return out.contiguous()
 
 
 class TwoStageInverseFilterBank:
-    """Inverts stage 2 only, per output coarse channel (TwoStageInverseFilterBank.m:75-157)."""
+    """Inverts stage 2 only, one inversion per output coarse channel - here one batched launch
+    (TwoStageInverseFilterBank.m:75-157)."""
 
     def __init__(self, cfg2: dict, nch2: int, stage2_nchan: int, combine=1, single=False):
         self.cfg2 = cfg2
         self.nch2, self.stage2_nchan = nch2, stage2_nchan
         self.combine, self.single = combine, single
-        self.stage2 = {}
+        self.inv = None
+        self.input_buffer = None
+        self.buffered_samples = 0
 
     def execute(self, x):
         torch = _torch()
@@ -197,16 +233,27 @@ class TwoStageInverseFilterBank:
         nch_out //= self.combine
         if self.single:
             nch_out = 1
-        out = None
-        for ich in range(nch_out):
-            if ich not in self.stage2:
-                self.stage2[ich] = InverseFilterBank(**self.cfg2)
-                if ich > 0:
-                    self.stage2[ich]._plans = self.stage2[0]._plans          # plans are stateless: share them
-            ifb = self.stage2[ich]
-            ifb.critical, ifb.combine = critical, self.combine
-            tmp = ifb.execute(x[:, ich * nch_in: (ich + 1) * nch_in, 0:1].contiguous())
-            if out is None:
-                out = torch.zeros((tmp.shape[0], nch_out, 1), dtype=tmp.dtype, device=tmp.device)
-            out[:, ich, 0] = tmp[:, 0]
-        return out
+        if self.inv is None:
+            self.inv = InverseFilterBank(**self.cfg2)
+        ifb = self.inv
+        ifb.critical, ifb.combine = critical, self.combine
+        if self.buffered_samples > 0:
+            x = torch.cat([self.input_buffer, x], dim=0)
+            self.buffered_samples = 0
+        x = x.contiguous()
+        n_dat = x.shape[0]
+        xg = x[:, : nch_out * nch_in, 0:1].reshape(n_dat, nch_out, nch_in, 1).contiguous()
+        out = ifb._plan(nch_in).batched(xg, sample_offset=ifb.sample_offset + 1)        # [n_out][nch_out][1]
+        nu, de = os_.nu, os_.de
+        while True:                                   # InverseFilterBank.m:104-124 (same for every group)
+            input_idat = out.shape[0] * nu // (nch_in * de)
+            self.buffered_samples = n_dat - input_idat
+            rem = self.buffered_samples % nu
+            if rem == 0:
+                break
+            self.buffered_samples += nu - rem
+            input_idat = n_dat - self.buffered_samples
+            out = out[: input_idat * (nch_in * de) // nu]
+        if self.buffered_samples > 0:
+            self.input_buffer = x[input_idat:].clone()
+        return out.contiguous()

@@ -90,6 +90,20 @@ class AnalysisPlan:
                                                  int(first_call), _stream_ptr(self.device)))
         return out
 
+    def batched(self, x, first_call=True, coarse_major=True):
+        """``x``: [n_dat, nstreams] independent single-pol streams (e.g. the coarse channels of a first
+        stage).  Returns [nblocks, nstreams, nchan_out] (coarse_major) or [nblocks, nchan_out, nstreams]."""
+        _check_tensor(x, self.dtype, self.device, 2)
+        n_dat, nstreams = x.shape
+        nb = self.nblocks(n_dat, first_call)
+        shape = (nb, nstreams, self.nchan_out) if coarse_major else (nb, self.nchan_out, nstreams)
+        out = torch.empty(shape, dtype=self.dtype, device=self.device)
+        with torch.cuda.device(self.device):
+            _l.check(_l.lib.pfb_analysis_execute_batched(self._h, x.data_ptr(), out.data_ptr(), nstreams, n_dat,
+                                                         int(first_call), 1 if coarse_major else 0,
+                                                         _stream_ptr(self.device)))
+        return out
+
     def segment(self, x_local, sample0, k_first, nblk, out=None, first_call=True):
         """Blocks [k_first, k_first+nblk) of the stream whose sample ``sample0`` is x_local[0]."""
         _check_tensor(x_local, self.dtype, self.device, 2)
@@ -192,6 +206,24 @@ class InversePlan:
         n = (ctypes.c_longlong * 2)()
         _l.check(_l.lib.pfb_inverse_get_profile(self._h, ms, n))
         return {"chan_idft": (ms[0], n[0]), "resample": (ms[1], n[1])}
+
+    def batched(self, x, sample_offset=1):
+        """``x``: [n_dat, ngroups, nchan, npol] - ngroups independent channel sets (the coarse channels of a
+        two-stage filterbank).  Returns the inverted series [n_out, ngroups, npol]."""
+        _check_tensor(x, self.dtype, self.device, 4)
+        if sample_offset > 1:
+            x = x[sample_offset - 1:]
+        n_dat, G, nchan, npol = x.shape
+        if nchan != self.nchan:
+            raise ValueError(f"plan built for {self.nchan} channels, data has {nchan}")
+        nblk = self.nblocks(n_dat)
+        keep2 = self.output_keep // self.nchan
+        tmp = torch.empty((nblk * keep2, G, nchan, npol), dtype=self.dtype, device=self.device)
+        with torch.cuda.device(self.device):
+            _l.check(_l.lib.pfb_inverse_execute_batched(self._h, x.data_ptr(), tmp.data_ptr(), G, npol, n_dat,
+                                                        _stream_ptr(self.device)))
+        # [T2][g][t1][pol] -> sample index T2*nchan + t1
+        return tmp.permute(0, 2, 1, 3).reshape(nblk * keep2 * nchan, G, npol)
 
     def stage(self, stage, x, out):
         n_dat, nchan, npol = x.shape
