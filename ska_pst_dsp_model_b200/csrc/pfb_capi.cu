@@ -148,7 +148,12 @@ struct pfb_analysis_plan {
   const void* d_taps = nullptr;     // T[fl]
   const void* d_low_taps = nullptr; // fast Low kernel tap layout
   bool low_fast = false;
+  void* d_yscratch = nullptr;       // arm sums of the sliding-window FIR kernel
+  size_t yscratch_cap = 0;
   DeviceTables tabs;
+  ~pfb_analysis_plan() {
+    if (d_yscratch) cudaFree(d_yscratch);
+  }
 };
 
 struct pfb_inverse_plan {
@@ -298,6 +303,53 @@ template <typename T> static int analysis_launch_generic(AnalysisArgs a, long lo
   return check_launch("pfb_analysis_generic");
 }
 
+// sliding-window FIR + FFT (two kernels) for the (taps per arm, de) pairs that have an instantiation
+template <typename T, int P, int DE>
+static int slide_go(pfb_analysis_plan* p, const AnalysisArgs& a, cudaStream_t st) {
+  const size_t need = (size_t)a.nblocks * a.N * a.npol * sizeof(Cx<T>);
+  if (need > p->yscratch_cap) {
+    if (p->d_yscratch) CU(cudaFree(p->d_yscratch));
+    p->d_yscratch = nullptr; p->yscratch_cap = 0;
+    CU(cudaMalloc(&p->d_yscratch, need));
+    p->yscratch_cap = need;
+  }
+  FirSlideArgs f;
+  memset(&f, 0, sizeof(f));
+  f.in = a.in; f.y = p->d_yscratch; f.taps = a.taps;
+  f.N = a.N; f.S = a.S; f.npol = a.npol; f.nu = p->nu;
+  f.n_dat = a.n_dat; f.start0 = a.start0; f.phase0 = a.phase0; f.nblocks = a.nblocks;
+  constexpr int PER = DE < P ? P / cgcd(P, DE) : 1;
+  const long long nsteps = (a.nblocks + p->nu - 1) / p->nu;
+  const unsigned gx = (unsigned)((a.N * a.npol + 255) / 256);
+  long long nseg = (148ll * 8) / ((long long)gx * p->nu);
+  if (nseg < 1) nseg = 1;
+  long long spc = (nsteps + nseg - 1) / nseg;
+  spc = (spc + PER - 1) / PER * PER;
+  nseg = (nsteps + spc - 1) / spc;
+  f.steps_per_cta = spc;
+  if (nseg > 65535) return fail(PFB_ERR_ARG, "too many segments");
+  pfb_fir_slide<T, P, DE><<<dim3(gx, (unsigned)p->nu, (unsigned)nseg), 256, 0, st>>>(f);
+  int rc = check_launch("pfb_fir_slide");
+  if (rc) return rc;
+  AnalysisArgs b = a;
+  b.ysrc = p->d_yscratch;
+  return analysis_launch_generic<T>(b, 0, a.nblocks, st);
+}
+
+template <typename T>
+static int analysis_launch_slide(pfb_analysis_plan* p, const AnalysisArgs& a, cudaStream_t st, bool* done) {
+  *done = true;
+  if (a.nblocks < 4 * p->nu) { *done = false; return PFB_OK; }
+  const int P = p->P, de = p->de;
+  if ((long long)p->nu * p->S != (long long)de * p->N) { *done = false; return PFB_OK; }   // needs N divisible by nu
+  if (P == 25 && de == 7) return slide_go<T, 25, 7>(p, a, st);       // SKA-Mid: 4096 ch, 8/7, 100 353 taps
+  if (P == 12 && de == 3) return slide_go<T, 12, 3>(p, a, st);       // SKA-Low shape outside the fast kernel (fp64, misaligned)
+  if (P == 13 && de == 3) return slide_go<T, 13, 3>(p, a, st);       // 3073-tap 'low' design
+  if (P == 24 && de == 27) return slide_go<T, 24, 27>(p, a, st);     // 'sps': 256 ch, 32/27, 6144 taps
+  *done = false;
+  return PFB_OK;
+}
+
 template <typename T> static int analysis_launch(pfb_analysis_plan* p, AnalysisArgs& a, cudaStream_t st) {
   if (a.nblocks <= 0) return PFB_OK;
   long long k_lo = 0, k_hi = 0;
@@ -309,7 +361,12 @@ template <typename T> static int analysis_launch(pfb_analysis_plan* p, AnalysisA
       if (rc) return rc;
     }
   }
-  if (k_hi <= k_lo) return analysis_launch_generic<T>(a, 0, a.nblocks, st);
+  if (k_hi <= k_lo) {
+    bool done = false;
+    int rc = analysis_launch_slide<T>(p, a, st, &done);
+    if (rc || done) return rc;
+    return analysis_launch_generic<T>(a, 0, a.nblocks, st);
+  }
   // head / tail blocks whose window leaves the resident samples (zero fill) stay on the generic kernel
   int rc = analysis_launch_generic<T>(a, 0, k_lo, st);
   if (rc) return rc;

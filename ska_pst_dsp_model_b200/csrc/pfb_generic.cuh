@@ -33,6 +33,8 @@ struct AnalysisArgs {
   // batched form: `in` holds in_pitch independent streams per time sample; blockIdx.y selects a tile of
   // npol of them; output element (k, chan, stream) lives at k*out_sk + chan*out_sc + stream*out_sp
   long long in_pitch, out_sk, out_sc, out_sp;
+  // two-kernel form: arm sums already computed by pfb_fir_slide into ysrc[k][slot][pol]
+  const void* ysrc;
 };
 
 template <typename T>
@@ -48,6 +50,15 @@ __global__ void __launch_bounds__(256) pfb_analysis_generic(const AnalysisArgs a
 
   // FIR: work item = (kk, j, pol), pol fastest -> coalesced over [t][pol]
   const int items = kb * N * npol;
+  if (a.ysrc) {
+    const Cx<T>* __restrict__ y = reinterpret_cast<const Cx<T>*>(a.ysrc) + k0 * (long long)N * npol;
+    for (int e = threadIdx.x; e < items; e += blockDim.x) {
+      const int pol = e % npol;
+      const int slot = (e / npol) % N;
+      const int kk = e / (npol * N);
+      s[(size_t)(kk * npol + pol) * ld + padi<T>(slot)] = ldg_cx<T>(y + e);
+    }
+  } else
   for (int e = threadIdx.x; e < items; e += blockDim.x) {
     const int pol = e % npol;
     const int j = (e / npol) % N;
@@ -83,6 +94,73 @@ __global__ void __launch_bounds__(256) pfb_analysis_generic(const AnalysisArgs a
     long long ko = k0 + kk + a.kout0;
     if (a.kout_mod > 0) ko %= a.kout_mod;
     out[ko * a.out_sk + ci * a.out_sc + (pol0 + pol) * a.out_sp] = v * scale;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// K1s: sliding-window polyphase FIR for long filters (SKA-Mid: 25 taps/arm over 4096 arms, the
+// taps do not fit shared memory).  Blocks k and k + nu read the same sub-stream
+// x[k0*S + j + N*q] shifted by `de` elements (nu*S = de*N), so a thread that owns (arm j, pol,
+// k mod nu) keeps its P taps and a P-element window in registers and fetches only `de` new
+// samples per output (de/P loads per MAC instead of 2).  The rotated arm sums go to a scratch
+// array y[k][slot][pol]; pfb_analysis_generic (ysrc != null) then runs the FFT + store.
+// ---------------------------------------------------------------------------
+struct FirSlideArgs {
+  const void* in;
+  void* y;
+  const void* taps;      // T[P*N]
+  int N, S, npol, nu;
+  long long n_dat, start0, phase0, nblocks;
+  long long steps_per_cta;
+};
+
+__host__ __device__ constexpr int cgcd(int a, int b) { return b == 0 ? a : cgcd(b, a % b); }
+
+template <typename T, int P, int DE>
+__global__ void __launch_bounds__(256) pfb_fir_slide(const FirSlideArgs a) {
+  constexpr int NEW0 = DE < P ? P - DE : 0;                // window elements [NEW0, P) are new each step
+  constexpr int PER = DE < P ? P / cgcd(P, DE) : 1;        // steps until the register rotation repeats
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= a.N * a.npol) return;
+  const int pol = e % a.npol, j = e / a.npol;
+  const int k0 = blockIdx.y;
+  const long long nsteps = (a.nblocks - k0 + a.nu - 1) / a.nu;
+  const long long i_begin = (long long)blockIdx.z * a.steps_per_cta;
+  const long long i_end = min(i_begin + a.steps_per_cta, nsteps);
+  if (i_begin >= i_end) return;
+  const T* __restrict__ f = reinterpret_cast<const T*>(a.taps);
+  const Cx<T>* __restrict__ x = reinterpret_cast<const Cx<T>*>(a.in);
+  Cx<T>* __restrict__ y = reinterpret_cast<Cx<T>*>(a.y);
+  T tap[P];
+#pragma unroll
+  for (int m = 0; m < P; ++m) tap[m] = __ldg(f + j + m * a.N);
+  const long long tbase = a.start0 + (long long)k0 * a.S + j;
+  auto ld = [&](long long q) {
+    const long long t = tbase + (long long)a.N * q;
+    return (t >= 0 && t < a.n_dat) ? ldg_cx<T>(x + t * a.npol + pol) : mk<T>((T)0, (T)0);
+  };
+  Cx<T> w[P];
+#pragma unroll
+  for (int m = 0; m < NEW0; ++m) w[m] = ld((long long)DE * i_begin + m);
+  for (long long i = i_begin; i < i_end; i += PER) {
+#pragma unroll
+    for (int sidx = 0; sidx < PER; ++sidx) {
+      if (i + sidx < i_end) {
+        const long long q0 = (long long)DE * (i + sidx);
+#pragma unroll
+        for (int m = NEW0; m < P; ++m) w[(DE * sidx + m) % P] = ld(q0 + m);
+        T ax = 0, ay = 0;
+#pragma unroll
+        for (int m = 0; m < P; ++m) {
+          const Cx<T> v = w[(DE * sidx + m) % P];
+          ax += tap[m] * v.x;
+          ay += tap[m] * v.y;
+        }
+        const long long k = k0 + (long long)a.nu * (i + sidx);
+        const int slot = pmod(a.phase0 + a.start0 + k * a.S + j, a.N);
+        y[(k * a.N + slot) * a.npol + pol] = mk<T>(ax, ay);
+      }
+    }
   }
 }
 
