@@ -134,11 +134,19 @@ __global__ void __launch_bounds__(256) pfb_fir_slide(const FirSlideArgs a) {
   T tap[P];
 #pragma unroll
   for (int m = 0; m < P; ++m) tap[m] = __ldg(f + j + m * a.N);
+  // sub-stream element q sits at sample tbase + N*q; valid (inside the resident samples) for q in [q_lo, q_hi)
   const long long tbase = a.start0 + (long long)k0 * a.S + j;
+  const long long q_lo = tbase >= 0 ? 0 : (-tbase + a.N - 1) / a.N;
+  const long long q_hi = tbase < a.n_dat ? (a.n_dat - tbase + a.N - 1) / a.N : 0;
+  const Cx<T>* __restrict__ xs = x + tbase * a.npol + pol;
+  const long long qstride = (long long)a.N * a.npol;
   auto ld = [&](long long q) {
-    const long long t = tbase + (long long)a.N * q;
-    return (t >= 0 && t < a.n_dat) ? ldg_cx<T>(x + t * a.npol + pol) : mk<T>((T)0, (T)0);
+    return (q >= q_lo && q < q_hi) ? ldg_cx<T>(xs + q * qstride) : mk<T>((T)0, (T)0);
   };
+  // nu*S = de*N: every block of this thread lands in the same FFT slot
+  const int slot = pmod(a.phase0 + a.start0 + (long long)k0 * a.S + j, a.N);
+  Cx<T>* __restrict__ yo = y + ((long long)k0 * a.N + slot) * a.npol + pol;
+  const long long ystride = (long long)a.nu * a.N * a.npol;
   Cx<T> w[P];
 #pragma unroll
   for (int m = 0; m < NEW0; ++m) w[m] = ld((long long)DE * i_begin + m);
@@ -156,9 +164,7 @@ __global__ void __launch_bounds__(256) pfb_fir_slide(const FirSlideArgs a) {
           ax += tap[m] * v.x;
           ay += tap[m] * v.y;
         }
-        const long long k = k0 + (long long)a.nu * (i + sidx);
-        const int slot = pmod(a.phase0 + a.start0 + k * a.S + j, a.N);
-        y[(k * a.N + slot) * a.npol + pol] = mk<T>(ax, ay);
+        yo[(i + sidx) * ystride] = mk<T>(ax, ay);
       }
     }
   }
