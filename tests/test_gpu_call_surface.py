@@ -178,3 +178,33 @@ def test_mid_config_round_trip_impulse(tmp_path):
     rest = np.abs(y).copy() / np.abs(y[pk])
     rest[pk - 1: pk + 2] = 0
     assert 20 * np.log10(rest.max()) < -60
+
+
+def test_matlab_cli_replacements(tmp_path, pst_taps):
+    """The reference's backend="matlab" path: subprocess of build/<exe> with positional argv (util.run_cmd)."""
+    import subprocess
+    import sys
+    from ska_pst_dsp_model_b200.formats import DADAFile
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    bindir = os.path.join(root, "ska_pst_dsp_model_b200", "bin")
+    d = str(tmp_path)
+    hdr = tmp_path / "hdr.json"
+    hdr.write_text('{"HDR_SIZE": "4096", "TSAMP": "0.025", "NCHAN": "1", "NPOL": "2", "NBIT": "32", "NDIM": "2"}')
+    taps = tmp_path / "taps.npy"
+    np.save(taps, pst_taps / pst_taps.sum())
+    n = 256 * 192 * 3
+    run = lambda *a: subprocess.run([sys.executable] + [str(x) for x in a], check=False, capture_output=True, text=True)
+    r = run(os.path.join(bindir, "generate_test_vector"), "time_domain_impulse", n, "0.25,1", "single", 2, hdr,
+            "imp.dump", d, 1)
+    assert r.returncode == 0, r.stderr
+    src = DADAFile(os.path.join(d, "imp.dump")).load_data()
+    assert src.data.shape == (n, 1, 2) and src.data[n // 4 - 1, 0, 0] == 1 and src.data.sum() == 2   # 1-based offset
+    r = run(os.path.join(bindir, "channelize"), src.file_path, 256, "4/3", taps, "chan.dump", d, 1, 0)
+    assert r.returncode == 0, r.stderr
+    r = run(os.path.join(bindir, "synthesize"), os.path.join(d, "chan.dump"), 256, "inv.dump", d, 1, 1, 1, 48, "tukey")
+    assert r.returncode == 0, r.stderr
+    y = DADAFile(os.path.join(d, "inv.dump")).load_data().data[:, 0, 0]
+    expect = (n // 4 - 1) - 1536 - 36 * 256
+    assert int(np.argmax(np.abs(y))) == expect
+    r = run(os.path.join(bindir, "channelize"), "/nonexistent.dump", 256, "4/3", taps, "x.dump", d)
+    assert r.returncode != 0                                             # -> RuntimeError in the reference's run_cmd
