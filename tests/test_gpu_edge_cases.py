@@ -93,12 +93,12 @@ def test_many_small_scratch_chunks_equal_one_chunk(pst_taps):
 
 
 def test_linearity_and_time_invariance_at_scale(pst_taps):
-    """Size-independent properties on a 2^22-sample stream (no oracle): linearity of the round trip and
-    invariance under a shift by one overlap-save hop (30720 samples)."""
+    """Size-independent properties at BASELINE's full size (dual-pol 2^24 samples, no oracle): linearity of
+    the round trip and invariance under a shift by one overlap-save hop (30720 samples)."""
     import torch
     from ska_pst_dsp_model_b200 import ops
     h = pst_taps / pst_taps.sum()
-    n = 1 << 22
+    n = 1 << 24
     g = torch.Generator(device="cuda").manual_seed(1)
     a = torch.view_as_complex(torch.randn((n, 2, 2), generator=g, device="cuda"))
     b = torch.view_as_complex(torch.randn((n, 2, 2), generator=g, device="cuda"))
