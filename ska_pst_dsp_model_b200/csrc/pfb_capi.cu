@@ -571,12 +571,13 @@ int pfb_inverse_set_scratch_bytes(pfb_inverse_plan* p, long long bytes) {
 }
 
 template <typename T>
-static int launch_chan_idft(pfb_inverse_plan* p, const void* in, void* out, int npol, long long nrows, cudaStream_t st) {
+static int launch_chan_idft(pfb_inverse_plan* p, const void* in, void* out, int npol, long long nrows, cudaStream_t st,
+                            bool grouped = false) {
   if (nrows <= 0) return PFB_OK;
   const int tok = p->prof_begin(0, st);
   if (p->low_fast) {
     bool done = false;
-    int rc = low_chan_idft_launch<T>(p->d_low, in, out, npol, nrows, st, &done);
+    int rc = low_chan_idft_launch<T>(p->d_low, in, out, npol, nrows, st, &done, grouped);
     if (rc) return fail(PFB_ERR_CUDA, "pfb_chan_idft_low launch: %s", cudaGetErrorString((cudaError_t)rc));
     if (done) { p->prof_end(tok, st); return check_launch("pfb_chan_idft_low"); }
   }
@@ -598,12 +599,12 @@ static int launch_chan_idft(pfb_inverse_plan* p, const void* in, void* out, int 
 
 template <typename T>
 static int launch_resample(pfb_inverse_plan* p, const void* v, void* out, int npol, long long nblk, cudaStream_t st,
-                           int G = 1) {
+                           int G = 1, bool grouped = false, long long rows_cap = 0) {
   if (nblk <= 0) return PFB_OK;
   const int tok = p->prof_begin(1, st);
   if (p->low_fast) {
     bool done = false;
-    int rc = low_resample_launch<T>(p->d_low, v, out, npol, nblk, G, st, &done);
+    int rc = low_resample_launch<T>(p->d_low, v, out, npol, nblk, G, st, &done, grouped, rows_cap);
     if (rc) return fail(PFB_ERR_CUDA, "pfb_resample_low launch: %s", cudaGetErrorString((cudaError_t)rc));
     if (done) { p->prof_end(tok, st); return check_launch("pfb_resample_low"); }
   }
@@ -665,10 +666,12 @@ static int inverse_run(pfb_inverse_plan* p, const void* in, void* out, int npol,
     const long long nb = (nblocks - n0 < B) ? nblocks - n0 : B;
     const long long rows = (nb - 1) * p->keep + p->Nf;
     const Cx<T>* src = reinterpret_cast<const Cx<T>*>(in) + n0 * p->keep * rowlen;
-    int rc = launch_chan_idft<T>(p, src, p->d_scratch, npol, rows * G, st);      // every (tau, group) is one row
-    if (rc) return rc;
     Cx<T>* dst = reinterpret_cast<Cx<T>*>(out) + n0 * p->keep2 * rowlen;
-    rc = launch_resample<T>(p, p->d_scratch, dst, npol, nb, st, G);
+    // SKA-Low dual-pol shape: grouped scratch layout + warp-autonomous resample kernel
+    const bool ws = p->low_fast && std::is_same<T, float>::value && low_ws_ok(p->d_low, npol, G, src, dst);
+    int rc = launch_chan_idft<T>(p, src, p->d_scratch, npol, rows * G, st, ws);  // every (tau, group) is one row
+    if (rc) return rc;
+    rc = launch_resample<T>(p, p->d_scratch, dst, npol, nb, st, G, ws, rows);
     if (rc) return rc;
   }
   return PFB_OK;

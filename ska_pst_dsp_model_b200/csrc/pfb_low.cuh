@@ -21,6 +21,7 @@
 //  * K2/K3 split the 256-point FFT 16 x 16 (and the 192-point inverse 12 x 16) over 16
 //    lanes per transform with in-register radix-16/12 butterflies and compile-time twiddles.
 #pragma once
+#include <cuda.h>
 #include <cstdlib>
 #include <type_traits>
 #include <vector>
@@ -288,10 +289,19 @@ __global__ void __launch_bounds__(64 * NPOL, NPOL == 2 ? 2 : 4) pfb_analysis_low
 // ===========================================================================
 struct ChanArgs {
   const C* in;          // [row][256][pol]
-  C* out;               // [row][256][pol]
+  C* out;               // [row][256][pol]  (or the grouped layout below)
   const float2* tw256;  // [256] exp(-2 pi i k/256)
   long long nrows;
+  long long rows_cap;   // grouped layout: rows per column group
 };
+
+// Grouped scratch layout read by pfb_resample_low_ws: the 256 columns t1 are split into 32 groups of
+// 8; group g holds its rows contiguously, one row = 8 x 16 B (both polarisations of one t1), and
+// the 16-byte unit of t1 sits at position (t1 & 7) ^ (row & 7), so that a plain bulk copy of
+// whole rows lands in shared memory already bank-swizzled for the column reads.
+__device__ __forceinline__ long long grouped_unit(long long rows_cap, long long row, int t1) {
+  return (((long long)(t1 >> 3) * rows_cap + row) << 3) + ((t1 & 7) ^ (int)(row & 7));
+}
 
 constexpr int kColStride = 273;   // 16*17 + 1, odd
 constexpr int kQStride = 17;
@@ -410,6 +420,7 @@ __global__ void __launch_bounds__(128, 4) pfb_chan_idft_low_p2(const ChanArgs a)
 // ring slot itself with __syncwarp() only - the CTA never executes a block-wide barrier.
 constexpr int kChanStages = 3;
 constexpr int kChanRows = 8;                      // rows per stage = 16 lanes x 8 = 128 threads
+template <bool GROUPED>
 __global__ void __launch_bounds__(128, 2) pfb_chan_idft_low_tma(const ChanArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float4* ring = reinterpret_cast<float4*>(smem_raw);                    // [stage][8 rows][273]
@@ -486,11 +497,12 @@ __global__ void __launch_bounds__(128, 2) pfb_chan_idft_low_tma(const ChanArgs a
       fft_reg<4, 4, +1>(x0);
       fft_reg<4, 4, +1>(x1);
       if (row < a.nrows) {
-        float4* p = reinterpret_cast<float4*>(a.out) + row * 256 + o;
+        float4* p = reinterpret_cast<float4*>(a.out) + (GROUPED ? grouped_unit(a.rows_cap, row, o) : row * 256 + o);
+        const long long step = GROUPED ? 16 * a.rows_cap : 16;      // t1 += 16: two groups further
 #pragma unroll
         for (int o2 = 0; o2 < 16; ++o2) {
           const C u0 = x0[slot<4, 4>(o2)], u1 = x1[slot<4, 4>(o2)];
-          p[o2 * 16] = make_float4(u0.x, u0.y, u1.x, u1.y);
+          p[o2 * step] = make_float4(u0.x, u0.y, u1.x, u1.y);
         }
       }
     }
@@ -636,6 +648,216 @@ __global__ void __launch_bounds__(16 * COLS, 512 / (16 * COLS)) pfb_resample_low
         }
       }
     }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// K3 (SKA-Low shape, dual-pol): warp-autonomous variant.
+//
+// One warp owns one t1 (both polarisations): lane = (q, pol), so the 16 lanes of a transform share
+// a warp and the two exchanges of the 16x16 / 12x16 passes need __syncwarp() only - no block-wide
+// barrier couples the 8 compute warps of a CTA.  Global memory is touched by the TMA engine alone:
+// a 9th (producer) warp streams the column group's rows from the grouped scratch layout
+// (grouped_unit above; one bulk copy per 160-row overlap-save step, double-buffered) and writes the
+// finished output rows back with bulk stores from a staging tile.  The 96-row overlap between
+// consecutive blocks never leaves the register file: 160 = 16 * 10, so elements i = 10..15 of
+// lane q in block n are elements i = 0..5 of the same lane in block n + 1.
+// ---------------------------------------------------------------------------
+constexpr int kWsWarps = 8;                           // compute warps = t1 per CTA
+constexpr int kWsRowBytes = kWsWarps * 16;            // 128 B: 8 t1 x 2 pol
+constexpr int kWsStepRows = 160;                      // keep = Nf - 2 ov
+constexpr int kWsSlots = 2;
+constexpr int kWsColStride = 280;                     // per-pol exchange buffer pitch: 560 words = 16 (mod 32)
+constexpr int kWsOutRows = 120;                       // keep2
+
+struct WsArgs {
+  const char* v;        // grouped scratch
+  char* out;            // [T2][256][2] complex64
+  const float* taper;   // [256]
+  const C* wt;          // [nchan][192]
+  const float2* tw256;
+  const float2* tw192;
+  long long rows_cap;   // rows per group in the scratch
+  int nchan;            // output row pitch in t1
+  int nblk, nsplit;
+};
+
+constexpr size_t ws_smem_bytes() {
+  return (size_t)kWsSlots * kWsStepRows * kWsRowBytes         // ring
+         + (size_t)kWsWarps * 2 * kWsColStride * sizeof(C)   // exchange
+         + (size_t)kWsOutRows * kWsRowBytes                  // output staging (tensor-map box, 128B swizzle)
+         + (size_t)kWsWarps * 192 * sizeof(C)                // weights
+         + (256 + 192) * sizeof(C) + 256 * sizeof(float)     // twiddles, taper
+         + 64;                                               // mbarriers
+}
+
+// one box [rows][128 B] of the staging tile -> global rows (x in fp32 elements, y in rows)
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, const void* ssrc, int x, int y) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(tm), "r"(x), "r"(y),
+               "r"(smem_u32(ssrc))
+               : "memory");
+}
+
+__global__ void __launch_bounds__(32 * (kWsWarps + 1), 2)
+    pfb_resample_low_ws(const WsArgs a, const __grid_constant__ CUtensorMap out_map) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* ring = smem_raw;                                              // [slot][160][128 B]
+  C* exch = reinterpret_cast<C*>(ring + kWsSlots * kWsStepRows * kWsRowBytes); // [warp][pol][280]
+  unsigned char* outs = reinterpret_cast<unsigned char*>(exch + kWsWarps * 2 * kWsColStride);   // [120][128 B], 1 KiB aligned
+  C* swt = reinterpret_cast<C*>(outs + kWsOutRows * kWsRowBytes);              // [8 t1][192]
+  C* t1s = swt + kWsWarps * 192;                                               // [16 o][16 q]
+  C* t2s = t1s + 256;                                                          // [12 m][16 o]
+  float* stp = reinterpret_cast<float*>(t2s + 192);                            // [256]
+  uint64_t* full = reinterpret_cast<uint64_t*>(stp + 256);                     // [2]
+  uint64_t* empty = full + kWsSlots;                                           // [2]
+  uint64_t* out_full = empty + kWsSlots;
+  uint64_t* out_free = out_full + 1;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int groups = a.nchan >> 3;
+  const int g = blockIdx.x % groups, sp = blockIdx.x / groups;
+  const int per = (a.nblk + a.nsplit - 1) / a.nsplit;
+  const int n_begin = sp * per, n_end = min(a.nblk, n_begin + per);
+  const int nb = n_end - n_begin;
+  if (nb <= 0) return;
+
+  if (tid == 0) {
+    for (int s = 0; s < kWsSlots; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kWsWarps); }
+    mbar_init(out_full, kWsWarps);
+    mbar_init(out_free, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+
+  const char* vgrp = a.v + ((long long)g * a.rows_cap + (long long)n_begin * kWsStepRows) * kWsRowBytes;
+  // load k: k = 0 is the 96-row head of the first block, k >= 1 the 160 new rows of block k - 1
+  auto issue = [&](int k) {
+    const uint32_t bytes = (k == 0 ? 96u : 160u) * kWsRowBytes;
+    const long long row0 = k == 0 ? 0 : (long long)(k - 1) * kWsStepRows + 96;
+    uint64_t* bar = &full[k & 1];
+    mbar_expect_tx(bar, bytes);
+    tma_load_1d(ring + (size_t)(k & 1) * kWsStepRows * kWsRowBytes, vgrp + row0 * kWsRowBytes, bytes, bar);
+  };
+  if (warp == kWsWarps && lane == 0) { issue(0); issue(1); }
+
+  // tables (all warps help)
+  for (int i = tid; i < kWsWarps * 192; i += blockDim.x) swt[i] = a.wt[(size_t)g * kWsWarps * 192 + i];
+  for (int i = tid; i < 256; i += blockDim.x) {
+    stp[i] = a.taper[i];
+    const float2 v = __ldg(a.tw256 + (((i >> 4) * (i & 15)) & 255));
+    t1s[i] = mk<float>(v.x, v.y);
+  }
+  for (int i = tid; i < 192; i += blockDim.x) {
+    const float2 v = __ldg(a.tw192 + (((i >> 4) * (i & 15)) % 192));
+    t2s[i] = mk<float>(v.x, v.y);
+  }
+  __syncthreads();
+
+  if (warp == kWsWarps) {
+    // ---------------- producer warp ----------------
+    if (lane != 0) return;
+    for (int b = 0; b < nb; ++b) {
+      if (b + 2 <= nb) {
+        mbar_wait(&empty[b & 1], (uint32_t)((b >> 1) & 1));      // load b consumed by every compute warp
+        issue(b + 2);
+      }
+      mbar_wait(out_full, (uint32_t)(b & 1));
+      tma_store_2d(&out_map, outs, g * (kWsRowBytes / 4), (n_begin + b) * kWsOutRows);
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      mbar_arrive(out_free);
+    }
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    return;
+  }
+
+  // ---------------- compute warps ----------------
+  const int q = lane >> 1, pol = lane & 1;
+  C* ex = exch + (size_t)(warp * 2 + pol) * kWsColStride;
+  const C* wrow = swt + warp * 192;
+  // byte offset of this lane's column inside a ring row: unit (t1l ^ (row & 7)), row & 7 == q & 7
+  const int coloff = ((warp ^ (q & 7)) << 4) + (pol << 3);
+
+  C carry[6];
+  {
+    mbar_wait(&full[0], 0);
+    const unsigned char* rp = ring + (size_t)q * kWsRowBytes + coloff;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) carry[i] = *reinterpret_cast<const C*>(rp + (size_t)i * 16 * kWsRowBytes);
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[0]);
+  }
+
+  for (int b = 0; b < nb; ++b) {
+    C x[16];
+    {
+      // phase 1: lane q holds tau = q + 16 i
+      const int k = b + 1;
+      mbar_wait(&full[k & 1], (uint32_t)((k >> 1) & 1));
+      const unsigned char* rp = ring + ((size_t)(k & 1) * kWsStepRows + q) * kWsRowBytes + coloff;
+#pragma unroll
+      for (int i = 0; i < 6; ++i) x[i] = carry[i];
+#pragma unroll
+      for (int i = 6; i < 16; ++i) x[i] = *reinterpret_cast<const C*>(rp + (size_t)(i - 6) * 16 * kWsRowBytes);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[k & 1]);
+#pragma unroll
+      for (int i = 0; i < 6; ++i) carry[i] = x[i + 10];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) x[i] = x[i] * stp[q + 16 * i];
+      fft_reg<4, 4, -1>(x);
+#pragma unroll
+      for (int o = 0; o < 16; ++o) {
+        C v = x[slot<4, 4>(o)];
+        if (o) v = v * t1s[o * 16 + q];
+        ex[o * kQStride + q] = v;
+      }
+    }
+    __syncwarp();
+    {
+      // phase 2: lane o = q: bins b = o + 16 o2; keep o2 in {0..5} U {10..15}
+      const int o = q;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) x[i] = ex[o * kQStride + i];
+      __syncwarp();
+      fft_reg<4, 4, -1>(x);
+      C z[12];
+#pragma unroll
+      for (int k = 0; k < 12; ++k) {
+        const int o2 = k < 6 ? k : k + 4;
+        const int bb = o + 16 * o2;
+        const int rr = bb < 96 ? bb + 96 : bb - 160;
+        z[k] = x[slot<4, 4>(o2)] * wrow[rr];
+      }
+      fft_reg<3, 4, +1>(z);
+#pragma unroll
+      for (int m = 0; m < 12; ++m) {
+        C v = z[slot<3, 4>(m)];
+        if (m) v = v * t2s[m * 16 + o];
+        ex[m * kQStride + o] = v;
+      }
+    }
+    __syncwarp();
+    if (q < 12) {
+      // phase 3: lane m = q: y[m + 12 j] = sum_o ex[m][o] exp(+2 pi i o j / 16); keep j in [3, 13)
+      const int m = q;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) x[i] = ex[m * kQStride + i];
+      fft_reg<4, 4, +1>(x);
+      if (b > 0) mbar_wait(out_free, (uint32_t)((b - 1) & 1));
+      // staging row r = m + 12 j - 36 (12 j - 36 = 0 (mod 8) for odd j, 4 for even j); the tensor map's 128B
+      // swizzle puts 16-byte unit u of a row at u ^ (address bits 7..9)
+      const int rb = m + (int)((smem_u32(outs) >> 7) & 7);
+      unsigned char* op0 = outs + (size_t)m * kWsRowBytes + ((warp ^ (rb & 7)) << 4) + (pol << 3);
+      unsigned char* op1 = outs + (size_t)m * kWsRowBytes + ((warp ^ ((rb + 4) & 7)) << 4) + (pol << 3);
+#pragma unroll
+      for (int j = 3; j < 13; ++j)
+        *reinterpret_cast<C*>(((j & 1) ? op0 : op1) + (12 * j - 36) * kWsRowBytes) = x[slot<4, 4>(j)];
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(out_full);
   }
 }
 
@@ -820,14 +1042,23 @@ inline int low_inverse_plan_init<float>(int nchan, int nu, int de, int Nf, int o
 }
 
 template <typename T>
-int low_chan_idft_launch(const void* d_low, const void* in, void* out, int npol, long long nrows, cudaStream_t st, bool* done) {
+int low_chan_idft_launch(const void* d_low, const void* in, void* out, int npol, long long nrows, cudaStream_t st, bool* done,
+                         bool grouped = false) {
   *done = false;
   return 0;
 }
 
+// true when the warp-autonomous resample kernel (and the grouped scratch layout it reads) applies
+inline bool low_ws_ok(const void* d_low, int npol, int groups_b, const void* in, const void* out) {
+  const low::LowInverse* h = reinterpret_cast<const low::LowInverse*>(d_low);
+  static const bool off = getenv("PFB_NO_WS") != nullptr;
+  return !off && h->chan_fast && npol == 2 && groups_b == 1 && h->ov2 == 36 && h->keep == 160 && !h->flip &&
+         ((uintptr_t)in % 16 == 0) && ((uintptr_t)out % 16 == 0);
+}
+
 template <>
 inline int low_chan_idft_launch<float>(const void* d_low, const void* in, void* out, int npol, long long nrows,
-                                       cudaStream_t st, bool* done) {
+                                       cudaStream_t st, bool* done, bool grouped) {
   *done = false;
   const low::LowInverse* h = reinterpret_cast<const low::LowInverse*>(d_low);
   if (!h->chan_fast) return 0;
@@ -848,9 +1079,18 @@ inline int low_chan_idft_launch<float>(const void* d_low, const void* in, void* 
     const size_t smem2 = (size_t)low::kChanStages * low::kChanRows * low::kColStride * sizeof(float4) + 64;
     const long long npass2 = (nrows + low::kChanRows - 1) / low::kChanRows;
     const long long grid2 = npass2 < (long long)sms * 2 ? npass2 : (long long)sms * 2;
-    e = cudaFuncSetAttribute(low::pfb_chan_idft_low_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
-    if (e != cudaSuccess) return (int)e;
-    low::pfb_chan_idft_low_tma<<<(unsigned)grid2, 128, smem2, st>>>(a);
+    a.rows_cap = nrows;
+    if (grouped) {
+      e = cudaFuncSetAttribute(low::pfb_chan_idft_low_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+      if (e != cudaSuccess) return (int)e;
+      low::pfb_chan_idft_low_tma<true><<<(unsigned)grid2, 128, smem2, st>>>(a);
+    } else {
+      e = cudaFuncSetAttribute(low::pfb_chan_idft_low_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+      if (e != cudaSuccess) return (int)e;
+      low::pfb_chan_idft_low_tma<false><<<(unsigned)grid2, 128, smem2, st>>>(a);
+    }
+  } else if (grouped) {
+    return (int)cudaErrorInvalidValue;
   } else if (npol == 2) {
     e = cudaFuncSetAttribute(low::pfb_chan_idft_low<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
@@ -872,23 +1112,67 @@ inline long long low_resample_nsplit(const void* d_low, int npol, int groups_b =
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int groups = h->nchan * groups_b / (16 / npol);   // 16 columns per CTA, 2 CTAs per SM
+  const int groups = h->nchan * groups_b / (16 / npol);   // 16 columns per CTA, 2 CTAs per SM (either resample kernel)
   long long n = ((long long)sms * 2) / groups;
   return n < 1 ? 1 : n;
 }
 
 template <typename T>
-int low_resample_launch(const void* d_low, const void* v, void* out, int npol, long long nblk, int groups_b, cudaStream_t st, bool* done) {
+int low_resample_launch(const void* d_low, const void* v, void* out, int npol, long long nblk, int groups_b, cudaStream_t st, bool* done,
+                        bool grouped = false, long long rows_cap = 0) {
   *done = false;
   return 0;
 }
 
 template <>
 inline int low_resample_launch<float>(const void* d_low, const void* v, void* out, int npol, long long nblk,
-                                      int groups_b, cudaStream_t st, bool* done) {
+                                      int groups_b, cudaStream_t st, bool* done, bool grouped, long long rows_cap) {
   *done = false;
   const low::LowInverse* h = reinterpret_cast<const low::LowInverse*>(d_low);
-  if (nblk > 2000000000ll) return 0;
+  if (nblk > 2000000000ll) return grouped ? (int)cudaErrorInvalidValue : 0;
+  if (grouped) {
+    low::WsArgs w;
+    w.v = reinterpret_cast<const char*>(v);
+    w.out = reinterpret_cast<char*>(out);
+    w.taper = h->taper; w.wt = h->wt; w.tw256 = h->tw256; w.tw192 = h->tw192;
+    w.rows_cap = rows_cap; w.nchan = h->nchan; w.nblk = (int)nblk;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int groups = h->nchan / low::kWsWarps;
+    long long ns = ((long long)sms * 2) / groups;     // one resident wave, 2 CTAs per SM
+    if (ns > nblk) ns = nblk;
+    if (ns < 1) ns = 1;
+    w.nsplit = (int)ns;
+    // tensor map of the output rows: [nblk * 120 rows][nchan * 4 fp32], box = 120 rows x 128 B
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn encode = nullptr;
+    if (!encode) {
+      void* fn = nullptr;
+      cudaDriverEntryPointQueryResult qres;
+      cudaError_t e0 = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+      if (e0 != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) return (int)cudaErrorNotSupported;
+      encode = reinterpret_cast<EncodeFn>(fn);
+    }
+    CUtensorMap tm;
+    const cuuint64_t gdim[2] = {(cuuint64_t)h->nchan * 4, (cuuint64_t)nblk * low::kWsOutRows};
+    const cuuint64_t gstride[1] = {(cuuint64_t)h->nchan * 16};
+    const cuuint32_t box[2] = {low::kWsRowBytes / 4, low::kWsOutRows};
+    const cuuint32_t estr[2] = {1, 1};
+    if (encode(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, out, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return (int)cudaErrorInvalidValue;
+    cudaError_t e = cudaFuncSetAttribute(low::pfb_resample_low_ws, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)low::ws_smem_bytes());
+    if (e != cudaSuccess) return (int)e;
+    low::pfb_resample_low_ws<<<(unsigned)(ns * groups), 32 * (low::kWsWarps + 1), low::ws_smem_bytes(), st>>>(w, tm);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return (int)e;
+    *done = true;
+    return 0;
+  }
   low::ResArgs a;
   a.v = reinterpret_cast<const low::C*>(v);
   a.out = reinterpret_cast<low::C*>(out);
