@@ -98,7 +98,8 @@ int pfb_inverse_execute_batched(pfb_inverse_plan* plan, const void* in_dev, void
  * n = nchan*FN_width doubles multiplying the stitched spectrum (NULL clears it).  With a taper set
  * the inversion runs the literal-order chain (per-channel FFT -> weights -> channel IDFT -> bin IFFT). */
 int pfb_inverse_set_spectral_taper(pfb_inverse_plan* plan, const double* taper, long long n);
-/* bytes of scratch between the two inversion kernels (default 128 MiB; <= ~64 MiB keeps it L2-resident) */
+/* bytes of scratch between the two inversion kernels (default 1 GiB: the whole stream in one chunk up to ~2^25
+ * samples/pol at the SKA-Low shape; longer streams are processed in chunks of whole overlap-save blocks) */
 int pfb_inverse_set_scratch_bytes(pfb_inverse_plan* plan, long long bytes);
 /* run only one stage of the chain over the whole input (profiling / roofline):
  * stage 0 = channel IDFT into the caller's v buffer [n_dat][nchan][npol],

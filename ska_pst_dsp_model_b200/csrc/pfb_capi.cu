@@ -168,7 +168,7 @@ struct pfb_inverse_plan {
   std::vector<double> deripple_w;    // FN-order deripple weights (kept for set_spectral_taper)
   const void* d_low = nullptr;       // fast-path tables (pfb_low.cuh)
   bool low_fast = false;
-  long long scratch_bytes = 128ll << 20;
+  long long scratch_bytes = 1024ll << 20;   // one chunk for streams up to ~2^25 samples/pol at the SKA-Low shape
   void* d_scratch = nullptr;
   size_t scratch_cap = 0;
   DeviceTables tabs;

@@ -698,6 +698,9 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, const void* 
                : "memory");
 }
 
+// UNITY_MID: the temporal taper is exactly 1 on [ov, Nf - ov) (Tukey, top-hat interior, no window), so only
+// the 6 edge samples of a lane are scaled.
+template <bool UNITY_MID>
 __global__ void __launch_bounds__(32 * (kWsWarps + 1), 2)
     pfb_resample_low_ws(const WsArgs a, const __grid_constant__ CUtensorMap out_map) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -805,7 +808,8 @@ __global__ void __launch_bounds__(32 * (kWsWarps + 1), 2)
 #pragma unroll
       for (int i = 0; i < 6; ++i) carry[i] = x[i + 10];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) x[i] = x[i] * stp[q + 16 * i];
+      for (int i = 0; i < 16; ++i)
+        if (!UNITY_MID || i < 3 || i >= 13) x[i] = x[i] * stp[q + 16 * i];      // ov = 48 = 3 * 16
       fft_reg<4, 4, -1>(x);
 #pragma unroll
       for (int o = 0; o < 16; ++o) {
@@ -870,6 +874,7 @@ struct LowInverse {
   const float2* tw256;
   const float2* tw192;
   int nchan, keep, ov2, keep2, flip, chan_fast;
+  bool taper_unity_mid;   // taper == 1 on [ov, Nf - ov)
 };
 
 template <typename U> inline int upload_raw(const std::vector<U>& h, std::vector<void*>* allocs, const U** out) {
@@ -1036,6 +1041,9 @@ inline int low_inverse_plan_init<float>(int nchan, int nu, int de, int Nf, int o
   h->nchan = nchan; h->keep = Nf - 2 * ov; h->ov2 = ov * de / nu; h->keep2 = 192 - 2 * h->ov2;
   h->flip = spans ? 0 : 1;
   h->chan_fast = (nchan == 256 && combine == 1) ? 1 : 0;
+  h->taper_unity_mid = true;
+  for (int i = ov; i < Nf - ov; ++i)
+    if (taper[(size_t)i] != 1.0f) h->taper_unity_mid = false;
   *d_low = h;
   *enabled = true;
   return 0;
@@ -1164,10 +1172,10 @@ inline int low_resample_launch<float>(const void* d_low, const void* v, void* ou
     if (encode(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, out, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
       return (int)cudaErrorInvalidValue;
-    cudaError_t e = cudaFuncSetAttribute(low::pfb_resample_low_ws, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)low::ws_smem_bytes());
+    auto kern = h->taper_unity_mid ? low::pfb_resample_low_ws<true> : low::pfb_resample_low_ws<false>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)low::ws_smem_bytes());
     if (e != cudaSuccess) return (int)e;
-    low::pfb_resample_low_ws<<<(unsigned)(ns * groups), 32 * (low::kWsWarps + 1), low::ws_smem_bytes(), st>>>(w, tm);
+    kern<<<(unsigned)(ns * groups), 32 * (low::kWsWarps + 1), low::ws_smem_bytes(), st>>>(w, tm);
     e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
     *done = true;

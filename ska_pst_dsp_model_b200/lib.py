@@ -10,7 +10,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpfb_b200.so")
+# PFB_B200_LIB selects another build of the same library (kernel experiments); the default is the in-tree build
+LIB_PATH = os.environ.get("PFB_B200_LIB") or os.path.join(_HERE, "libpfb_b200.so")
 
 EXPORTS = [
     "pfb_last_error", "pfb_version", "pfb_launch_count",

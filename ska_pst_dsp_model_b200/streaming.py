@@ -1,6 +1,10 @@
 """Host-resident streams: analysis + inversion with the H2D copy, the kernels and
 the D2H copy of successive time segments overlapped on three CUDA streams.
 
+The whole step (every copy and kernel of every segment, with its cross-stream dependencies) is
+captured once per pair of host buffers into a CUDA graph and replayed with a single launch, so the
+host cost per segment does not limit how finely the stream can be cut.
+
 This is the executor behind the end-to-end number (`e2e` in bench.py) and the
 file-level operators for large inputs: the reference moves data between stages
 only as files / host arrays (python/data_gen/pipeline.py:62-84), so a drop-in
@@ -15,7 +19,7 @@ from .sharding import plan_time_shards
 
 class HostRoundTrip:
     def __init__(self, n_dat, nchan, os_factor, taps, input_fft_length, input_overlap, temporal_taper="tukey",
-                 deripple=True, npol=2, nseg=16, dtype=None, device=None, k_total=None):
+                 deripple=True, npol=2, nseg=16, dtype=None, device=None, k_total=None, use_graph=True):
         import torch
         from . import ops
         self.torch = torch
@@ -44,10 +48,34 @@ class HostRoundTrip:
         self.dchan = [torch.empty((mx_fine, nchan, npol), dtype=dtype, device=dev) for _ in range(2)]
         self.dout = [torch.empty((mx_out, npol), dtype=dtype, device=dev) for _ in range(2)]
         self.s_in, self.s_cmp, self.s_out = (torch.cuda.Stream(dev) for _ in range(3))
+        self.use_graph = use_graph
+        self._graphs = {}         # (x.data_ptr, y.data_ptr) -> captured step
+        self._warm = False
 
     def run(self, x_host, y_host):
         """x_host: pinned [n_dat, npol]; y_host: pinned [n_out, npol]. Returns after the work is
         enqueued; the caller's current stream waits for the last D2H copy."""
+        torch = self.torch
+        if not self.use_graph:
+            return self._enqueue(x_host, y_host)
+        key = (x_host.data_ptr(), y_host.data_ptr())
+        g = self._graphs.get(key)
+        if g is None:
+            if not self._warm:                      # first pass eagerly: the plans size their scratch here
+                self._enqueue(x_host, y_host)
+                torch.cuda.current_stream(self.device).synchronize()
+                self._warm = True
+            g = torch.cuda.CUDAGraph()
+            cap = torch.cuda.Stream(self.device)
+            cap.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.graph(g, stream=cap, capture_error_mode="thread_local"):
+                self._enqueue(x_host, y_host)
+            torch.cuda.current_stream(self.device).wait_stream(cap)
+            self._graphs[key] = g
+        g.replay()
+        return y_host
+
+    def _enqueue(self, x_host, y_host):
         torch = self.torch
         cur = torch.cuda.current_stream(self.device)
         for s in (self.s_in, self.s_cmp, self.s_out):

@@ -64,7 +64,7 @@ def test_single_pol_fast_path_and_odd_length(pst_taps):
 
 
 def test_inverse_stages_compose(pst_taps):
-    """pfb_inverse_execute_stage(0) then (1) over a full-size v buffer == pfb_inverse_execute."""
+    """pfb_inverse_execute_stage(0) then (1) over a full-size v buffer agrees with pfb_inverse_execute (1e-6)."""
     import torch
     from ska_pst_dsp_model_b200 import ops
     rng = np.random.default_rng(4)
@@ -74,7 +74,10 @@ def test_inverse_stages_compose(pst_taps):
     inv.stage(0, x, v)
     out = torch.empty((inv.out_len(x.shape[0]), 2), dtype=torch.complex64, device="cuda")
     inv.stage(1, v, out)
-    assert torch.equal(out, inv(x))
+    # the one-call path uses the TMA-streamed resample kernel on a grouped scratch layout, the staged
+    # path the natural-layout kernels: same arithmetic, different instruction schedule (FMA contraction)
+    ref = inv(x)
+    assert float((out - ref).abs().max() / ref.abs().max()) < 1e-6
     # stage 0 alone is an un-normalised inverse DFT across channels
     ref = np.fft.ifft(x[:5].cpu().numpy(), axis=1) * 256
     assert nerr(v[:5].cpu().numpy(), ref) < 1e-5
