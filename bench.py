@@ -443,7 +443,7 @@ def main():
     ap.add_argument("--cpu-log2-samples", type=int, default=22, help="bounded CPU sample per pol")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--e2e-segments", type=int, default=16)
-    ap.add_argument("--scratch-mib", type=int, default=0, help="override the L2-resident inversion scratch size")
+    ap.add_argument("--scratch-mib", type=int, default=0, help="override the inversion scratch cap (default 1 GiB: one chunk)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
