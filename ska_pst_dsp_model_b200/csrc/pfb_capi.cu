@@ -13,6 +13,7 @@
 #include "../../include/pfb_b200.h"
 #include "pfb_generic.cuh"
 #include "pfb_low.cuh"
+#include "pfb_mid.cuh"
 #include "pfb_purity.cuh"
 
 using namespace pfb;
@@ -331,6 +332,17 @@ static int slide_go(pfb_analysis_plan* p, const AnalysisArgs& a, cudaStream_t st
   pfb_fir_slide<T, P, DE><<<dim3(gx, (unsigned)p->nu, (unsigned)nseg), 256, 0, st>>>(f);
   int rc = check_launch("pfb_fir_slide");
   if (rc) return rc;
+  if (std::is_same<T, float>::value && a.N == 4096 && a.npol == 2 && ((uintptr_t)a.out % 16 == 0) &&
+      !getenv("PFB_NO_MID")) {
+    // 4096-channel fast path: one register-resident 16x16x16 transform per (block, both pols)
+    mid::RowFftArgs m;
+    m.in = p->d_yscratch; m.out = a.out; m.tw = reinterpret_cast<const float2*>(a.fft.tw); m.jmap = nullptr;
+    m.nrows = a.nblocks; m.kout0 = a.kout0; m.kout_mod = a.kout_mod;
+    m.chan_first = a.chan_first; m.nchan_out = a.nchan_out; m.scale = (float)a.scale;
+    rc = mid::rowfft4096_launch<-1, true>(m, st);
+    if (rc) return fail(PFB_ERR_CUDA, "pfb_rowfft4096 launch: %s", cudaGetErrorString((cudaError_t)rc));
+    return check_launch("pfb_rowfft4096");
+  }
   AnalysisArgs b = a;
   b.ysrc = p->d_yscratch;
   return analysis_launch_generic<T>(b, 0, a.nblocks, st);
@@ -580,6 +592,16 @@ static int launch_chan_idft(pfb_inverse_plan* p, const void* in, void* out, int 
     int rc = low_chan_idft_launch<T>(p->d_low, in, out, npol, nrows, st, &done, grouped);
     if (rc) return fail(PFB_ERR_CUDA, "pfb_chan_idft_low launch: %s", cudaGetErrorString((cudaError_t)rc));
     if (done) { p->prof_end(tok, st); return check_launch("pfb_chan_idft_low"); }
+  }
+  if (std::is_same<T, float>::value && p->nchan == 4096 && npol == 2 && ((uintptr_t)in % 16 == 0) &&
+      ((uintptr_t)out % 16 == 0) && !getenv("PFB_NO_MID")) {
+    mid::RowFftArgs m;
+    memset(&m, 0, sizeof(m));
+    m.in = in; m.out = out; m.tw = reinterpret_cast<const float2*>(p->fft_chan.tw); m.jmap = p->d_jmap; m.nrows = nrows;
+    int rc = mid::rowfft4096_launch<+1, false>(m, st);
+    if (rc) return fail(PFB_ERR_CUDA, "pfb_rowfft4096 launch: %s", cudaGetErrorString((cudaError_t)rc));
+    p->prof_end(tok, st);
+    return check_launch("pfb_rowfft4096");
   }
   ChanIdftArgs a;
   memset(&a, 0, sizeof(a));

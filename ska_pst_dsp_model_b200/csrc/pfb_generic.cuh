@@ -150,21 +150,31 @@ __global__ void __launch_bounds__(256) pfb_fir_slide(const FirSlideArgs a) {
   Cx<T> w[P];
 #pragma unroll
   for (int m = 0; m < NEW0; ++m) w[m] = ld((long long)DE * i_begin + m);
+  // the new samples of a step are fetched one step ahead (their latency hides behind the MACs of the
+  // current step), and the MACs run as four independent chains
+  constexpr int NNEW = P - NEW0;
+  Cx<T> nx[NNEW];
+#pragma unroll
+  for (int m = 0; m < NNEW; ++m) nx[m] = ld((long long)DE * i_begin + NEW0 + m);
   for (long long i = i_begin; i < i_end; i += PER) {
 #pragma unroll
     for (int sidx = 0; sidx < PER; ++sidx) {
       if (i + sidx < i_end) {
-        const long long q0 = (long long)DE * (i + sidx);
 #pragma unroll
-        for (int m = NEW0; m < P; ++m) w[(DE * sidx + m) % P] = ld(q0 + m);
-        T ax = 0, ay = 0;
+        for (int m = 0; m < NNEW; ++m) w[(DE * sidx + NEW0 + m) % P] = nx[m];
+        if (i + sidx + 1 < i_end) {
+          const long long q1 = (long long)DE * (i + sidx + 1) + NEW0;
+#pragma unroll
+          for (int m = 0; m < NNEW; ++m) nx[m] = ld(q1 + m);
+        }
+        T ax0 = 0, ay0 = 0, ax1 = 0, ay1 = 0;
 #pragma unroll
         for (int m = 0; m < P; ++m) {
           const Cx<T> v = w[(DE * sidx + m) % P];
-          ax += tap[m] * v.x;
-          ay += tap[m] * v.y;
+          if (m & 1) { ax1 += tap[m] * v.x; ay1 += tap[m] * v.y; }
+          else { ax0 += tap[m] * v.x; ay0 += tap[m] * v.y; }
         }
-        yo[(i + sidx) * ystride] = mk<T>(ax, ay);
+        yo[(i + sidx) * ystride] = mk<T>(ax0 + ax1, ay0 + ay1);
       }
     }
   }

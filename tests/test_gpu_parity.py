@@ -86,6 +86,7 @@ def test_analysis_bunton(nchan, osf, ntaps, extra, npol, dt, pst_taps):
     (8, "4/3", 50, 999, 1),
     (512, "8/7", 512 * 24 + 1, 448 * 40 + 11, 2),
     (4096, "8/7", 4096 * 2 + 1, 3584 * 6, 1),
+    (4096, "8/7", 4096 * 24 + 1, 3584 * 41 + 7, 2),      # SKA-Mid shape: sliding-window FIR<25,7> + 16x16x16 row FFT
 ])
 def test_analysis_padded(nchan, osf, ntaps, ndat, npol, dt):
     from ska_pst_dsp_model_b200 import ops
@@ -124,6 +125,8 @@ INVERSE_CASES = [
     (256, "32/27", 256, 32, True, 1, True, "tukey", 3, 2),
     (512, "8/7", 512, 128, True, 1, True, "tukey", 3, 2),
     (4096, "8/7", 512, 128, True, 1, False, "tukey", 2, 1),
+    (4096, "8/7", 512, 128, True, 1, True, "tukey", 2, 2),      # SKA-Mid dual-pol: 4096-point row FFT as channel IDFT
+    (4096, "8/7", 128, 16, False, 16, False, "tukey", 2, 2),    # ... with the combine re-order on its loads
     (256, "4/3", 1024, 128, True, 1, True, "tukey", 2, 2),
 ]
 
