@@ -319,17 +319,17 @@ static int slide_go(pfb_analysis_plan* p, const AnalysisArgs& a, cudaStream_t st
   f.in = a.in; f.y = p->d_yscratch; f.taps = a.taps;
   f.N = a.N; f.S = a.S; f.npol = a.npol; f.nu = p->nu;
   f.n_dat = a.n_dat; f.start0 = a.start0; f.phase0 = a.phase0; f.nblocks = a.nblocks;
-  constexpr int PER = DE < P ? P / cgcd(P, DE) : 1;
+  constexpr int PER = DE < P ? (P + DE - 1) / DE : 1;     // unroll period of the kernel's circular window
   const long long nsteps = (a.nblocks + p->nu - 1) / p->nu;
-  const unsigned gx = (unsigned)((a.N * a.npol + 255) / 256);
-  long long nseg = (148ll * 8) / ((long long)gx * p->nu);
+  const unsigned gx = (unsigned)((a.N * a.npol + 127) / 128);
+  long long nseg = (148ll * 12) / ((long long)gx * p->nu);
   if (nseg < 1) nseg = 1;
   long long spc = (nsteps + nseg - 1) / nseg;
   spc = (spc + PER - 1) / PER * PER;
   nseg = (nsteps + spc - 1) / spc;
   f.steps_per_cta = spc;
   if (nseg > 65535) return fail(PFB_ERR_ARG, "too many segments");
-  pfb_fir_slide<T, P, DE><<<dim3(gx, (unsigned)p->nu, (unsigned)nseg), 256, 0, st>>>(f);
+  pfb_fir_slide<T, P, DE><<<dim3(gx, (unsigned)p->nu, (unsigned)nseg), 128, 0, st>>>(f);
   int rc = check_launch("pfb_fir_slide");
   if (rc) return rc;
   if (std::is_same<T, float>::value && a.N == 4096 && a.npol == 2 && ((uintptr_t)a.out % 16 == 0) &&

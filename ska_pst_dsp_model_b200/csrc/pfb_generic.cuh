@@ -2,6 +2,7 @@
 // These are the always-correct path; the Low-specific fast kernels live in
 // pfb_low.cuh and are selected by the plan when the shape matches.
 #pragma once
+#include <type_traits>
 #include "fft_smem.cuh"
 
 namespace pfb {
@@ -117,9 +118,13 @@ struct FirSlideArgs {
 __host__ __device__ constexpr int cgcd(int a, int b) { return b == 0 ? a : cgcd(b, a % b); }
 
 template <typename T, int P, int DE>
-__global__ void __launch_bounds__(256) pfb_fir_slide(const FirSlideArgs a) {
-  constexpr int NEW0 = DE < P ? P - DE : 0;                // window elements [NEW0, P) are new each step
-  constexpr int PER = DE < P ? P / cgcd(P, DE) : 1;        // steps until the register rotation repeats
+__global__ void __launch_bounds__(128, sizeof(T) == 4 ? 3 : 2) pfb_fir_slide(const FirSlideArgs a) {
+  // The window lives in a circular register file of W >= P slots with W a multiple of DE, so the
+  // rotation repeats every W / DE steps (4 for the SKA-Mid shape) and only that many steps are unrolled.
+  constexpr int NNEW = DE < P ? DE : P;                    // new window elements per step
+  constexpr int NEW0 = P - NNEW;                           // logical window elements [NEW0, P) are new each step
+  constexpr int W = DE < P ? (P + DE - 1) / DE * DE : P;
+  constexpr int PER = DE < P ? W / DE : 1;
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= a.N * a.npol) return;
   const int pol = e % a.npol, j = e / a.npol;
@@ -140,44 +145,48 @@ __global__ void __launch_bounds__(256) pfb_fir_slide(const FirSlideArgs a) {
   const long long q_hi = tbase < a.n_dat ? (a.n_dat - tbase + a.N - 1) / a.N : 0;
   const Cx<T>* __restrict__ xs = x + tbase * a.npol + pol;
   const long long qstride = (long long)a.N * a.npol;
+  // every element this thread will touch is resident: unchecked loads off a running pointer
+  const bool interior = (long long)DE * i_begin >= q_lo && (long long)DE * (i_end - 1) + P <= q_hi;
   auto ld = [&](long long q) {
     return (q >= q_lo && q < q_hi) ? ldg_cx<T>(xs + q * qstride) : mk<T>((T)0, (T)0);
   };
   // nu*S = de*N: every block of this thread lands in the same FFT slot
   const int slot = pmod(a.phase0 + a.start0 + (long long)k0 * a.S + j, a.N);
-  Cx<T>* __restrict__ yo = y + ((long long)k0 * a.N + slot) * a.npol + pol;
+  Cx<T>* __restrict__ yo = y + ((long long)k0 * a.N + slot) * a.npol + pol + i_begin * ((long long)a.nu * a.N * a.npol);
   const long long ystride = (long long)a.nu * a.N * a.npol;
-  Cx<T> w[P];
+  Cx<T> w[W];
 #pragma unroll
   for (int m = 0; m < NEW0; ++m) w[m] = ld((long long)DE * i_begin + m);
-  // the new samples of a step are fetched one step ahead (their latency hides behind the MACs of the
-  // current step), and the MACs run as four independent chains
-  constexpr int NNEW = P - NEW0;
-  Cx<T> nx[NNEW];
+  const Cx<T>* __restrict__ pn = xs + ((long long)DE * i_begin + NEW0) * qstride;     // first new element of the step
+  const long long pstep = (long long)DE * qstride;
+
+  auto run = [&](auto checked) {
+    constexpr bool CHECK = decltype(checked)::value;
+    for (long long i = i_begin; i < i_end; i += PER) {
 #pragma unroll
-  for (int m = 0; m < NNEW; ++m) nx[m] = ld((long long)DE * i_begin + NEW0 + m);
-  for (long long i = i_begin; i < i_end; i += PER) {
+      for (int sidx = 0; sidx < PER; ++sidx) {
+        if (i + sidx < i_end) {
 #pragma unroll
-    for (int sidx = 0; sidx < PER; ++sidx) {
-      if (i + sidx < i_end) {
+          for (int m = 0; m < NNEW; ++m) {
+            if (CHECK) w[(DE * sidx + NEW0 + m) % W] = ld((long long)DE * (i + sidx) + NEW0 + m);
+            else w[(DE * sidx + NEW0 + m) % W] = ldg_cx<T>(pn + m * qstride);
+          }
+          pn += pstep;
+          T ax0 = 0, ay0 = 0, ax1 = 0, ay1 = 0;              // two independent chains per component
 #pragma unroll
-        for (int m = 0; m < NNEW; ++m) w[(DE * sidx + NEW0 + m) % P] = nx[m];
-        if (i + sidx + 1 < i_end) {
-          const long long q1 = (long long)DE * (i + sidx + 1) + NEW0;
-#pragma unroll
-          for (int m = 0; m < NNEW; ++m) nx[m] = ld(q1 + m);
+          for (int m = 0; m < P; ++m) {
+            const Cx<T> v = w[(DE * sidx + m) % W];
+            if (m & 1) { ax1 += tap[m] * v.x; ay1 += tap[m] * v.y; }
+            else { ax0 += tap[m] * v.x; ay0 += tap[m] * v.y; }
+          }
+          *yo = mk<T>(ax0 + ax1, ay0 + ay1);
+          yo += ystride;
         }
-        T ax0 = 0, ay0 = 0, ax1 = 0, ay1 = 0;
-#pragma unroll
-        for (int m = 0; m < P; ++m) {
-          const Cx<T> v = w[(DE * sidx + m) % P];
-          if (m & 1) { ax1 += tap[m] * v.x; ay1 += tap[m] * v.y; }
-          else { ax0 += tap[m] * v.x; ay0 += tap[m] * v.y; }
-        }
-        yo[(i + sidx) * ystride] = mk<T>(ax0 + ax1, ay0 + ay1);
       }
     }
-  }
+  };
+  if (interior) run(std::false_type());
+  else run(std::true_type());
 }
 
 // ---------------------------------------------------------------------------
