@@ -105,6 +105,10 @@ __global__ void __launch_bounds__(256) pfb_analysis_generic(const AnalysisArgs a
 // k mod nu) keeps its P taps and a P-element window in registers and fetches only `de` new
 // samples per output (de/P loads per MAC instead of 2).  The rotated arm sums go to a scratch
 // array y[k][slot][pol]; pfb_analysis_generic (ysrc != null) then runs the FFT + store.
+// Measured bound (SKA-Mid, ncu): the nu = 8 block phases read the same sub-streams at different offsets, so
+// the input crosses L2 -> SM eight times (537 MB per 2^22 x 2 pol launch, ~5 TB/s); a TMA-fed ring per
+// (64 arms, phase) CTA was tried and is no faster for that reason.  Sharing the rows between the phases of
+// one CTA (32 arms x 8 phases x 2 pols) is the next step.
 // ---------------------------------------------------------------------------
 struct FirSlideArgs {
   const void* in;

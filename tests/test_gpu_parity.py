@@ -62,6 +62,7 @@ ANALYSIS_CASES = [
     (64, "1/1", 64 * 4, 64 * 30, 1),
     (512, "8/7", 512 * 5 + 1, 448 * 12, 2),
     (4096, "8/7", 4096 * 3 - 5, 3584 * 4 + 100, 2),
+    (256, "4/3", 3073, 192 * 150 + 11, 2),               # 'low' 3073-tap design: sliding-window FIR<13,3>
 ]
 
 
@@ -86,7 +87,7 @@ def test_analysis_bunton(nchan, osf, ntaps, extra, npol, dt, pst_taps):
     (8, "4/3", 50, 999, 1),
     (512, "8/7", 512 * 24 + 1, 448 * 40 + 11, 2),
     (4096, "8/7", 4096 * 2 + 1, 3584 * 6, 1),
-    (4096, "8/7", 4096 * 24 + 1, 3584 * 41 + 7, 2),      # SKA-Mid shape: sliding-window FIR<25,7> + 16x16x16 row FFT
+    (4096, "8/7", 4096 * 24 + 1, 3584 * 230 + 7, 2),     # SKA-Mid shape: sliding-window FIR<25,7> + 16x16x16 row FFT
 ])
 def test_analysis_padded(nchan, osf, ntaps, ndat, npol, dt):
     from ska_pst_dsp_model_b200 import ops
