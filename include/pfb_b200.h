@@ -120,6 +120,10 @@ int pfb_inverse_get_profile(pfb_inverse_plan* plan, double* ms2, long long* laun
  * phase=p1 [rad], bin_offset=p2); every polarisation gets the same signal; out: [n][npol]. */
 int pfb_generate_test_vector(int kind, void* out_dev, long long n, int npol, int dtype, double p0,
                              double p1, double p2, void* stream);
+/* same signal written to out[t * stride] only: lets the batch driver place two independent test vectors in the
+ * two polarisation slots of one [n][2] stream, so that a pair runs through the dual-pol kernels in one pass */
+int pfb_generate_test_vector_strided(int kind, void* out_dev, long long n, long long stride, int dtype,
+                                     double p0, double p1, double p2, void* stream);
 /* args_dev: device array of nvec records {const void* a; const void* b; long long n, stride_a, stride_b;
  * double scale_b; double* out;} (56 bytes each).  For every record one CTA reduces the series b (and the
  * reference a, may be NULL) and writes out[0..7] = sum|b-a|, max|b-a|, sum|b|^2, largest |b|^2,

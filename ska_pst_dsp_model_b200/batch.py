@@ -4,7 +4,9 @@ The reference's purity driver (python/verify/purity.py:165-207) runs one
 generate -> channelize -> synthesize -> compare pass per test vector through files on disk.
 Here every vector is synthesised on the device (``pfb_generate_test_vector``), channelized and
 inverted by the CUDA kernels, and reduced to the report's metrics by ``pfb_purity_metrics``;
-only ~8 doubles per vector leave the GPU.  Vectors are independent: across GPUs they are dealt
+only ~8 doubles per vector leave the GPU.  Two independent vectors ride in the two polarisation slots
+of one [n][2] stream (``pfb_generate_test_vector_strided``), so every pair goes through the dual-pol
+kernels in a single analysis + inversion pass.  Vectors are independent: across GPUs they are dealt
 round-robin (replicas, no data-path collective) and the per-vector records are gathered at the end.
 """
 from __future__ import annotations
@@ -47,9 +49,10 @@ class BatchPurity:
         dev, n = self.device, self.n_samples
         nb = self.analysis.nblocks(n)
         self.n_out = self.inverse.out_len(nb)
-        self.x = torch.empty((self.vb, n, 1), dtype=torch.complex64, device=dev)
-        self.ch = torch.empty((nb, channels, 1), dtype=torch.complex64, device=dev)
-        self.y = torch.empty((self.vb, self.n_out, 1), dtype=torch.complex64, device=dev)
+        self.vb += self.vb & 1                                    # whole pairs
+        self.x = torch.empty((self.vb // 2, n, 2), dtype=torch.complex64, device=dev)
+        self.ch = torch.empty((nb, channels, 2), dtype=torch.complex64, device=dev)
+        self.y = torch.empty((self.vb // 2, self.n_out, 2), dtype=torch.complex64, device=dev)
         self.met = torch.zeros((self.vb, 2, 8), dtype=torch.float64, device=dev)
         self.n_cmp = min(n - self.total_sample_shift, self.n_out)
 
@@ -69,29 +72,42 @@ class BatchPurity:
         with torch.cuda.device(self.device):
             for b0 in range(0, len(params), self.vb):
                 chunk = params[b0: b0 + self.vb]
+                npair = (len(chunk) + 1) // 2
                 for i, prm in enumerate(chunk):
-                    _l.check(_l.lib.pfb_generate_test_vector(kind, self.x[i].data_ptr(), self.n_samples, 1,
-                                                             _l.PFB_DTYPE_C64, *prm, self._stream()))
-                    self.analysis(self.x[i], out=self.ch)
-                    self.inverse(self.ch, out=self.y[i])
+                    # vector i -> polarisation slot i & 1 of pair i >> 1
+                    _l.check(_l.lib.pfb_generate_test_vector_strided(kind, self.x[i >> 1].data_ptr() + (i & 1) * esz,
+                                                                     self.n_samples, 2, _l.PFB_DTYPE_C64, *prm,
+                                                                     self._stream()))
+                if len(chunk) & 1:                    # odd tail: the spare slot repeats the last vector
+                    _l.check(_l.lib.pfb_generate_test_vector_strided(kind, self.x[npair - 1].data_ptr() + esz,
+                                                                     self.n_samples, 2, _l.PFB_DTYPE_C64, *chunk[-1],
+                                                                     self._stream()))
+                for pi in range(npair):
+                    self.analysis(self.x[pi], out=self.ch)
+                    self.inverse(self.ch, out=self.y[pi])
                 shift = self.total_sample_shift
                 recs = np.zeros(2 * len(chunk), dtype=_REC)
                 keep = []
+
+                def xa(i):
+                    return self.x[i >> 1].data_ptr() + (shift * 2 + (i & 1)) * esz
+
+                def yb(i):
+                    return self.y[i >> 1].data_ptr() + (i & 1) * esz
+
                 if kind == 0:
                     for i in range(len(chunk)):
-                        recs[2 * i] = (self.x[i].data_ptr() + shift * esz, self.y[i].data_ptr(), self.n_cmp, 1, 1, 1.0,
-                                       self.met[i, 0].data_ptr())
+                        recs[2 * i] = (xa(i), yb(i), self.n_cmp, 2, 2, 1.0, self.met[i, 0].data_ptr())
                         recs[2 * i + 1] = recs[2 * i]
                         recs[2 * i + 1]["out"] = self.met[i, 1].data_ptr()
                 else:
-                    fa = torch.fft.fft(self.x[: len(chunk), shift: shift + self.fft_size, 0] / self.fft_size, dim=1)
-                    fb = torch.fft.fft(self.y[: len(chunk), : self.fft_size, 0] / self.fft_size, dim=1)
+                    fa = torch.fft.fft(self.x[:npair, shift: shift + self.fft_size] / self.fft_size, dim=1).contiguous()
+                    fb = torch.fft.fft(self.y[:npair, : self.fft_size] / self.fft_size, dim=1).contiguous()
                     keep = [fa, fb]
                     for i in range(len(chunk)):
-                        recs[2 * i] = (self.x[i].data_ptr() + shift * esz, self.y[i].data_ptr(), self.n_cmp, 1, 1, 1.0,
-                                       self.met[i, 0].data_ptr())
-                        recs[2 * i + 1] = (fa[i].data_ptr(), fb[i].data_ptr(), self.fft_size, 1, 1, 1.0,
-                                           self.met[i, 1].data_ptr())
+                        recs[2 * i] = (xa(i), yb(i), self.n_cmp, 2, 2, 1.0, self.met[i, 0].data_ptr())
+                        recs[2 * i + 1] = (fa[i >> 1].data_ptr() + (i & 1) * esz, fb[i >> 1].data_ptr() + (i & 1) * esz,
+                                           self.fft_size, 2, 2, 1.0, self.met[i, 1].data_ptr())
                 keep.append(self._metrics(recs))
                 m = self.met[: len(chunk)].cpu().numpy()
                 del keep

@@ -875,12 +875,13 @@ int pfb_inverse_execute_stage(pfb_inverse_plan* p, int stage, const void* in_dev
 
 // ---------------------------------------------------------------------------
 // test vectors + purity reductions on device
-int pfb_generate_test_vector(int kind, void* out_dev, long long n, int npol, int dtype, double p0, double p1, double p2,
-                             void* stream) {
-  if (!out_dev || n < 0 || npol < 1 || (kind != 0 && kind != 1)) return fail(PFB_ERR_ARG, "pfb_generate_test_vector: bad argument");
+static int generate_run(int kind, void* out_dev, long long n, int npol, long long stride, int dtype, double p0, double p1,
+                        double p2, void* stream) {
+  if (!out_dev || n < 0 || npol < 1 || stride < npol || (kind != 0 && kind != 1))
+    return fail(PFB_ERR_ARG, "pfb_generate_test_vector: bad argument");
   if (n == 0) return PFB_OK;
   GenArgs a;
-  a.out = out_dev; a.n = n; a.npol = npol; a.kind = kind; a.p0 = p0; a.p1 = p1; a.p2 = p2;
+  a.out = out_dev; a.n = n; a.npol = npol; a.stride = stride; a.kind = kind; a.p0 = p0; a.p1 = p1; a.p2 = p2;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   long long grid = (n + 255) / 256;
   if (grid > 148 * 16) grid = 148 * 16;
@@ -888,6 +889,16 @@ int pfb_generate_test_vector(int kind, void* out_dev, long long n, int npol, int
   else if (dtype == PFB_DTYPE_C128) pfb_generate_kernel<double><<<(unsigned)grid, 256, 0, st>>>(a);
   else return fail(PFB_ERR_ARG, "dtype must be 0 (c64) or 1 (c128)");
   return check_launch("pfb_generate_kernel");
+}
+
+int pfb_generate_test_vector(int kind, void* out_dev, long long n, int npol, int dtype, double p0, double p1, double p2,
+                             void* stream) {
+  return generate_run(kind, out_dev, n, npol, npol, dtype, p0, p1, p2, stream);
+}
+
+int pfb_generate_test_vector_strided(int kind, void* out_dev, long long n, long long stride, int dtype, double p0,
+                                     double p1, double p2, void* stream) {
+  return generate_run(kind, out_dev, n, 1, stride, dtype, p0, p1, p2, stream);
 }
 
 int pfb_purity_metrics(const void* args_dev, int nvec, int dtype, void* stream) {

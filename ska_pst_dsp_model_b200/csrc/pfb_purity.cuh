@@ -9,8 +9,9 @@
 namespace pfb {
 
 struct GenArgs {
-  void* out;            // [n][npol] complex
+  void* out;            // [n][stride] complex; the first npol entries of every row are written
   long long n;
+  long long stride;
   int npol, kind;       // 0 impulse, 1 tone
   double p0, p1, p2;    // impulse: offset, width;  tone: frequency (bins), phase (rad), bin offset
 };
@@ -32,7 +33,7 @@ __global__ void __launch_bounds__(256) pfb_generate_kernel(const GenArgs a) {
       v.x = (T)c;
       v.y = (T)s;
     }
-    for (int p = 0; p < a.npol; ++p) out[t * a.npol + p] = v;
+    for (int p = 0; p < a.npol; ++p) out[t * a.stride + p] = v;
   }
 }
 
