@@ -304,6 +304,39 @@ template <typename T> static int analysis_launch_generic(AnalysisArgs a, long lo
   return check_launch("pfb_analysis_generic");
 }
 
+// phase-sharing FIR (pfb_mid.cuh): instantiated for the SKA-Mid shape (25 taps per arm, 8/7)
+template <typename T, int P, int DE> static bool fir_phases_applies(int nu) {
+  return std::is_same<T, float>::value && P == 25 && DE == 7 && nu == 8;
+}
+template <int P, int DE>
+static int fir_phases_launch(int nu, const AnalysisArgs& a, void* y, long long row0, long long rows_full, long long i1,
+                             cudaStream_t st) {
+  return (int)cudaErrorNotSupported;
+}
+template <>
+int fir_phases_launch<25, 7>(int nu, const AnalysisArgs& a, void* y, long long row0, long long rows_full, long long i1,
+                             cudaStream_t st) {
+  CUtensorMap tm;
+  int rc = mid::make_in_map(a.in, a.N, rows_full, 7, &tm);
+  if (rc) return rc;
+  mid::FirPhasesArgs f;
+  f.y = y; f.taps = reinterpret_cast<const float*>(a.taps);
+  f.N = a.N; f.S = a.S; f.nu = nu; f.start0 = a.start0; f.phase0 = a.phase0; f.nblocks = a.nblocks;
+  f.i0 = 0; f.i1 = i1; f.row0 = row0;
+  const int gx = a.N / mid::kPhArms;
+  long long nseg = (148ll * 2 * 4 + gx - 1) / gx;          // ~4 waves of two CTAs per SM
+  if (nseg < 1) nseg = 1;
+  long long spc = (i1 + nseg - 1) / nseg;
+  if (spc < 16) spc = 16;
+  nseg = (i1 + spc - 1) / spc;
+  f.steps_per_cta = spc;
+  constexpr size_t smem = mid::fir_phases_smem<25, 7>();
+  cudaError_t e = cudaFuncSetAttribute(mid::pfb_fir_phases<25, 7, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  mid::pfb_fir_phases<25, 7, 8><<<dim3((unsigned)gx, (unsigned)nseg), 2 * mid::kPhArms * 8 + 32, smem, st>>>(f, tm);
+  return (int)cudaGetLastError();
+}
+
 // sliding-window FIR + FFT (two kernels) for the (taps per arm, de) pairs that have an instantiation
 template <typename T, int P, int DE>
 static int slide_go(pfb_analysis_plan* p, const AnalysisArgs& a, cudaStream_t st) {
@@ -322,15 +355,39 @@ static int slide_go(pfb_analysis_plan* p, const AnalysisArgs& a, cudaStream_t st
   constexpr int PER = DE < P ? (P + DE - 1) / DE : 1;     // unroll period of the kernel's circular window
   const long long nsteps = (a.nblocks + p->nu - 1) / p->nu;
   const unsigned gx = (unsigned)((a.N * a.npol + 127) / 128);
-  long long nseg = (148ll * 12) / ((long long)gx * p->nu);
-  if (nseg < 1) nseg = 1;
-  long long spc = (nsteps + nseg - 1) / nseg;
-  spc = (spc + PER - 1) / PER * PER;
-  nseg = (nsteps + spc - 1) / spc;
-  f.steps_per_cta = spc;
-  if (nseg > 65535) return fail(PFB_ERR_ARG, "too many segments");
-  pfb_fir_slide<T, P, DE><<<dim3(gx, (unsigned)p->nu, (unsigned)nseg), 128, 0, st>>>(f);
-  int rc = check_launch("pfb_fir_slide");
+  auto launch_slide = [&](long long i0, long long i1) -> int {
+    if (i1 <= i0) return PFB_OK;
+    const long long n = i1 - i0;
+    long long nseg = (148ll * 12) / ((long long)gx * p->nu);
+    if (nseg < 1) nseg = 1;
+    long long spc = (n + nseg - 1) / nseg;
+    spc = (spc + PER - 1) / PER * PER;
+    nseg = (n + spc - 1) / spc;
+    if (nseg > 65535) return fail(PFB_ERR_ARG, "too many segments");
+    f.steps_per_cta = spc; f.i0 = i0; f.i1 = i1;
+    pfb_fir_slide<T, P, DE><<<dim3(gx, (unsigned)p->nu, (unsigned)nseg), 128, 0, st>>>(f);
+    return check_launch("pfb_fir_slide");
+  };
+  // fp32 dual-pol long filters whose block-0 window starts on a multiple of N samples: the phase-sharing kernel
+  // for every step whose rows lie in the whole-row part of the stream; the last few steps keep the checked loads
+  long long i_fast = 0;
+  if (fir_phases_applies<T, P, DE>(p->nu) && a.npol == 2 && a.N % mid::kPhArms == 0 && a.start0 % a.N == 0 &&
+      ((uintptr_t)a.in % 16 == 0) && !getenv("PFB_NO_MID")) {
+    const long long rows_full = a.n_dat / a.N;
+    const long long row0 = a.start0 / a.N;                       // exact (may be negative)
+    // step i reads rows row0 + Q, Q <= (nu - 1) + DE * i + P - 1
+    const long long qmax = rows_full - 1 - row0 - (p->nu - 1) - (P - 1);
+    i_fast = qmax >= 0 ? qmax / DE + 1 : 0;
+    if (i_fast > nsteps) i_fast = nsteps;
+    if (i_fast < 8) i_fast = 0;
+    if (i_fast > 0) {
+      int rc2 = fir_phases_launch<P, DE>(p->nu, a, p->d_yscratch, row0, rows_full, i_fast, st);
+      if (rc2) return fail(PFB_ERR_CUDA, "pfb_fir_phases launch: %s", cudaGetErrorString((cudaError_t)rc2));
+      rc2 = check_launch("pfb_fir_phases");
+      if (rc2) return rc2;
+    }
+  }
+  int rc = launch_slide(i_fast, nsteps);
   if (rc) return rc;
   if (std::is_same<T, float>::value && a.N == 4096 && a.npol == 2 && ((uintptr_t)a.out % 16 == 0) &&
       !getenv("PFB_NO_MID")) {

@@ -117,6 +117,7 @@ struct FirSlideArgs {
   int N, S, npol, nu;
   long long n_dat, start0, phase0, nblocks;
   long long steps_per_cta;
+  long long i0, i1;      // step range [i0, i1) of this launch (a step = one block of every phase k0)
 };
 
 __host__ __device__ constexpr int cgcd(int a, int b) { return b == 0 ? a : cgcd(b, a % b); }
@@ -134,8 +135,8 @@ __global__ void __launch_bounds__(128, sizeof(T) == 4 ? 3 : 2) pfb_fir_slide(con
   const int pol = e % a.npol, j = e / a.npol;
   const int k0 = blockIdx.y;
   const long long nsteps = (a.nblocks - k0 + a.nu - 1) / a.nu;
-  const long long i_begin = (long long)blockIdx.z * a.steps_per_cta;
-  const long long i_end = min(i_begin + a.steps_per_cta, nsteps);
+  const long long i_begin = a.i0 + (long long)blockIdx.z * a.steps_per_cta;
+  const long long i_end = min(min(i_begin + a.steps_per_cta, a.i1), nsteps);
   if (i_begin >= i_end) return;
   const T* __restrict__ f = reinterpret_cast<const T*>(a.taps);
   const Cx<T>* __restrict__ x = reinterpret_cast<const Cx<T>*>(a.in);

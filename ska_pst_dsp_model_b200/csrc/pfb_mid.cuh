@@ -139,5 +139,177 @@ inline int rowfft4096_launch(const RowFftArgs& a, cudaStream_t st) {
   return (int)cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------
+// Sliding-window polyphase FIR with the block phases sharing their input (fp32, dual-pol, long filters).
+//
+// nu*S = de*N, so block k = k0 + nu*i of output arm j reads the sub-stream of SAMPLE arm
+// a = (j - k0*(N - S)) mod N at rows Q = s + de*i + m, s = k0 - [a + k0*(N - S) >= N]: all nu phases walk the
+// same rows, s rows apart.  pfb_fir_slide gives every phase its own CTA, so the input crosses L2 -> SM nu
+// times; here one CTA owns 16 sample arms x 2 pols x nu phases, the rows (16 arms x 2 pols = 256 B each, N
+// samples apart) are fetched ONCE by the TMA engine (one 2-D tensor copy per group of `de` rows; rows before
+// the stream are zero-filled by the tensor map) into a shared ring, and every thread takes its `de` new
+// window elements per step from there.  Taps and the circular register window are as in pfb_fir_slide.
+// Requires the window start of block 0 to fall on a multiple of N samples.
+// ---------------------------------------------------------------------------
+constexpr int kPhArms = 16;                            // sample arms per CTA (x 2 pols x nu phases = 256 compute threads)
+constexpr int kPhGroups = 9;                           // ring depth in row groups
+
+struct FirPhasesArgs {
+  void* y;               // [k][slot][2]
+  const float* taps;     // [P*N]
+  int N, S, nu;
+  long long start0, phase0, nblocks;
+  long long i0, i1;      // step range of this launch; a step = one block of every phase
+  long long steps_per_cta;
+  long long row0;        // start0 / N (exact): tensor row of sub-stream row Q = 0
+};
+
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, int x, int y, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                   low::smem_u32(dst)),
+               "l"(tm), "r"(x), "r"(y), "r"(low::smem_u32(bar))
+               : "memory");
+}
+
+template <int P, int DE, int NU>
+__global__ void __launch_bounds__(2 * kPhArms * NU + 32, 2)
+    pfb_fir_phases(const FirPhasesArgs a, const __grid_constant__ CUtensorMap in_map) {
+  static_assert(DE < P, "long filters only");
+  constexpr int NEW0 = P - DE;
+  constexpr int W = (P + DE - 1) / DE * DE;
+  constexpr int PER = W / DE;
+  constexpr int NWARP = 2 * kPhArms * NU / 32;                    // compute warps
+  constexpr int kRowC = kPhArms * 2;                              // complex elements per row
+  constexpr uint32_t kGroupBytes = DE * kRowC * sizeof(C);
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  C* ring = reinterpret_cast<C*>(smem_raw);                       // [kPhGroups + 1][DE][64]: the last group mirrors group 0
+  uint64_t* full = reinterpret_cast<uint64_t*>(ring + (kPhGroups + 1) * DE * kRowC);
+  uint64_t* empty = full + kPhGroups;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int a0 = blockIdx.x * kPhArms;                            // first sample arm of the CTA
+  const long long nsteps_max = (a.nblocks + a.nu - 1) / a.nu;
+  const long long i_begin = a.i0 + (long long)blockIdx.y * a.steps_per_cta;
+  const long long i_end = min(min(i_begin + a.steps_per_cta, a.i1), nsteps_max);
+  if (i_begin >= i_end) return;
+  if (tid == 0) {
+    for (int s = 0; s < kPhGroups; ++s) { low::mbar_init(&full[s], 1); low::mbar_init(&empty[s], NWARP); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+  // virtual steps v = i_begin - (PER - 1) .. i_end - 1: the first PER - 1 only fill the register window
+  const long long v0 = i_begin - (PER - 1);
+  // row groups are numbered from the first one any thread reads: group gi holds rows DE*(g0 + gi) .. + DE - 1,
+  // g0 = v0 + NEW0 / DE (may be negative: rows before the stream, zero-filled)
+  const long long g0 = v0 + NEW0 / DE;
+  const long long ngroups = ((NU - 1) + (long long)DE * (i_end - 1 - v0) + NEW0 % DE + DE - 1) / DE + 1;
+
+  if (warp == NWARP) {
+    if (lane != 0) return;
+    for (long long gi = 0; gi < ngroups; ++gi) {
+      const int sl = (int)(gi % kPhGroups);
+      if (gi >= kPhGroups) low::mbar_wait(&empty[sl], (uint32_t)((gi / kPhGroups - 1) & 1));
+      // slot 0 is written twice (also behind the last slot) so that a thread's DE consecutive rows never wrap
+      low::mbar_expect_tx(&full[sl], sl == 0 ? 2 * kGroupBytes : kGroupBytes);
+      tma_load_2d(ring + sl * DE * kRowC, &in_map, a0 * 4, (int)(a.row0 + (g0 + gi) * DE), &full[sl]);
+      if (sl == 0)
+        tma_load_2d(ring + kPhGroups * DE * kRowC, &in_map, a0 * 4, (int)(a.row0 + (g0 + gi) * DE), &full[sl]);
+    }
+    return;
+  }
+
+  const int k0 = tid / (2 * kPhArms);                             // block phase
+  const int al = (tid % (2 * kPhArms)) >> 1, pol = tid & 1;                  // sample arm inside the group, polarisation
+  const int jj = a0 + al + k0 * (a.N - a.S);
+  const int c = jj >= a.N ? 1 : 0;
+  const int j = jj - c * a.N;                                     // output arm
+  const int s = k0 - c;                                           // row shift of this phase: 0 .. NU - 1
+  float tap[P];
+#pragma unroll
+  for (int m = 0; m < P; ++m) tap[m] = __ldg(a.taps + j + m * a.N);
+  const int slot = pmod(a.phase0 + a.start0 + (long long)k0 * a.S + j, a.N);
+  const long long ystride = (long long)a.nu * a.N * 2;
+  C* __restrict__ yo = reinterpret_cast<C*>(a.y) + ((long long)k0 * a.N + slot) * 2 + pol;
+  const C* myring = ring + al * 2 + pol;
+
+  C w[W];
+  const int nv = (int)(i_end - v0);                               // virtual steps of this CTA (32-bit loop state)
+  const int vskip = PER - 1;                                      // fill-only steps
+  const int kmax = (int)min((long long)nv, (a.nblocks - k0 + a.nu - 1) / a.nu - v0);   // steps that produce a block
+  yo += v0 * ystride;
+  // the DE new rows of a step start r0 rows into group gA and gA advances by exactly one group per step, so the
+  // ring position, the two barrier slots and their parities are carried incrementally (no divisions in the loop)
+  const int q0 = s + NEW0 % DE;
+  int gA = q0 / DE;                                               // relative group of the first new row
+  const int r0 = q0 - gA * DE;
+  int sA = gA % kPhGroups;
+  uint32_t parA = (uint32_t)((gA / kPhGroups) & 1);
+  auto step = [&](auto sidx_c, int vv) {
+    constexpr int sidx = decltype(sidx_c)::value;
+    const int sB = sA + 1 == kPhGroups ? 0 : sA + 1;
+    low::mbar_wait(&full[sA], parA);
+    if (r0 != 0) low::mbar_wait(&full[sB], sB == 0 ? parA ^ 1u : parA);
+    const C* pr = myring + (sA * DE + r0) * kRowC;                // rows pr[0 .. DE): slot 0 is mirrored behind slot G - 1
+#pragma unroll
+    for (int m = 0; m < DE; ++m) w[(DE * sidx + NEW0 + m) % W] = pr[m * kRowC];
+    __syncwarp();
+    // group gA - 1 was last touched by this warp one step ago: release it (every group exactly once)
+    if (lane == 0 && gA >= 1) low::mbar_arrive(&empty[sA == 0 ? kPhGroups - 1 : sA - 1]);
+    if (vv >= vskip && vv < kmax) {
+      float ax0 = 0, ay0 = 0, ax1 = 0, ay1 = 0;
+#pragma unroll
+      for (int m = 0; m < P; ++m) {
+        const C x = w[(DE * sidx + m) % W];
+        if (m & 1) { ax1 += tap[m] * x.x; ay1 += tap[m] * x.y; }
+        else { ax0 += tap[m] * x.x; ay0 += tap[m] * x.y; }
+      }
+      *yo = mk<float>(ax0 + ax1, ay0 + ay1);
+    }
+    yo += ystride;
+    ++gA;
+    if (++sA == kPhGroups) { sA = 0; parA ^= 1u; }
+  };
+  static_assert(PER == 4, "the unrolled step sequence below is written for a 4-step rotation");
+  int v = 0;
+  for (; v + PER <= nv; v += PER) {                               // whole rotations: straight-line code
+    step(std::integral_constant<int, 0>(), v);
+    step(std::integral_constant<int, 1>(), v + 1);
+    step(std::integral_constant<int, 2>(), v + 2);
+    step(std::integral_constant<int, 3>(), v + 3);
+  }
+  if (v < nv) step(std::integral_constant<int, 0>(), v);
+  if (v + 1 < nv) step(std::integral_constant<int, 1>(), v + 1);
+  if (v + 2 < nv) step(std::integral_constant<int, 2>(), v + 2);
+}
+
+template <int P, int DE> constexpr size_t fir_phases_smem() {
+  return (size_t)(kPhGroups + 1) * DE * kPhArms * 2 * sizeof(C) + 2 * kPhGroups * sizeof(uint64_t);
+}
+
+// tensor map of the input stream seen as rows of N samples: [rows][N * 4 fp32], box = 16 arms x 2 pols x `de` rows
+inline int make_in_map(const void* in, int N, long long rows, int de, CUtensorMap* tm) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e0 = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e0 != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) return (int)cudaErrorNotSupported;
+    encode = reinterpret_cast<EncodeFn>(fn);
+  }
+  const cuuint64_t gdim[2] = {(cuuint64_t)N * 4, (cuuint64_t)rows};
+  const cuuint64_t gstride[1] = {(cuuint64_t)N * 16};
+  const cuuint32_t box[2] = {kPhArms * 4, (cuuint32_t)de};
+  const cuuint32_t estr[2] = {1, 1};
+  if (encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(in), gdim, gstride, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return (int)cudaErrorInvalidValue;
+  return 0;
+}
+
 }  // namespace mid
 }  // namespace pfb

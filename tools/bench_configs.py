@@ -59,7 +59,7 @@ if "--skip-mid" not in sys.argv:
     res["cfg3"] = {"shape": f"4096 ch, OS 8/7, {hm.size} taps (padded), Nf=512, ov=128, 2^22 x 2 pol",
                    "filter_design_s": t_design, "inverse_plan_s": t_plan, "analysis_ms": ms_a, "inversion_ms": ms_i,
                    "analysis_Msamples_s": 2 * n / ms_a / 1e3, "round_trip_Msamples_s": 2 * n / (ms_a + ms_i) / 1e3,
-                   "nblocks": int(chm.shape[0]), "kernels": "pfb_fir_slide + pfb_rowfft4096 (analysis), pfb_rowfft4096 + generic resample (inversion)"}
+                   "nblocks": int(chm.shape[0]), "kernels": "pfb_fir_phases + pfb_rowfft4096 (analysis), pfb_rowfft4096 + generic resample (inversion)"}
     del xm, chm, ana, inv
 # cfg5: batched purity sweep
 nvec = int(os.environ.get("NVEC", "512"))
