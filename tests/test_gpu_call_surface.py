@@ -208,3 +208,42 @@ def test_matlab_cli_replacements(tmp_path, pst_taps):
     assert int(np.argmax(np.abs(y))) == expect
     r = run(os.path.join(bindir, "channelize"), "/nonexistent.dump", 256, "4/3", taps, "x.dump", d)
     assert r.returncode != 0                                             # -> RuntimeError in the reference's run_cmd
+
+
+def test_strided_generator_fills_one_polarisation_slot():
+    """pfb_generate_test_vector_strided writes out[t * stride] only (two vectors share one [n][2] stream)."""
+    import ctypes
+    import torch
+    from ska_pst_dsp_model_b200 import data_gen
+    from ska_pst_dsp_model_b200 import lib as L
+    n = 4096
+    x = torch.full((n, 2), 7 + 7j, dtype=torch.complex64, device="cuda")
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    L.check(L.lib.pfb_generate_test_vector_strided(0, x.data_ptr() + 8, n, 2, 0, 100.0, 2.0, 0.0, st))
+    got = x.cpu().numpy()
+    assert np.all(got[:, 0] == 7 + 7j)
+    assert np.array_equal(got[:, 1], data_gen.time_domain_impulse(n, [100], [2]))
+    L.check(L.lib.pfb_generate_test_vector_strided(1, x.data_ptr(), n, 2, 0, 5.0, 0.3, 0.0, st))
+    assert np.abs(x.cpu().numpy()[:, 0] - data_gen.complex_sinusoid(n, [5], [0.3], 0.0)).max() < 2e-7
+
+
+def test_host_round_trip_graph_replay_matches_eager(pst_taps):
+    """streaming.HostRoundTrip: the captured CUDA graph replays the same result as the eager segment loop and as the
+    one-shot device-resident plans (segments are cut on inversion-block boundaries, so the match is exact)."""
+    import torch
+    from ska_pst_dsp_model_b200 import ops
+    from ska_pst_dsp_model_b200.streaming import HostRoundTrip
+    h = pst_taps / pst_taps.sum()
+    rng = np.random.default_rng(11)
+    n = 3072 + 192 * (160 * 24 + 96)
+    x = torch.from_numpy((rng.standard_normal((n, 2)) + 1j * rng.standard_normal((n, 2))).astype(np.complex64)).pin_memory()
+    ref = ops.InversePlan(256, "4/3", 256, 48, "tukey", deripple_taps=h)(ops.AnalysisPlan(256, "4/3", h)(x.cuda())).cpu()
+    for use_graph in (False, True):
+        hrt = HostRoundTrip(n, 256, "4/3", h, 256, 48, "tukey", True, 2, nseg=4, use_graph=use_graph)
+        y = torch.zeros((hrt.n_out, 2), dtype=torch.complex64).pin_memory()
+        for _ in range(2):                       # second call replays the graph
+            y.zero_()
+            hrt.run(x, y)
+            torch.cuda.synchronize()
+            assert tuple(y.shape) == tuple(ref.shape)
+            assert torch.equal(y, ref), use_graph
