@@ -294,6 +294,13 @@ template <typename T> static int analysis_launch_generic(AnalysisArgs a, long lo
   const int ld = padded_len<T>(a.N);
   int kb = 4096 / (a.N * a.npol);
   if (kb < 1) kb = 1;
+  // few-channel filterbanks (cfg1: 8 channels, 384 taps per arm): shrink the CTA's block run until the grid
+  // covers the machine (the FIR loop is the cost, not the tiny FFTs)
+  {
+    const long long want = 148ll * 4;
+    const long long cap = (a.nblocks + want - 1) / want;
+    if (kb > cap) kb = (int)(cap < 1 ? 1 : cap);
+  }
   a.kb = kb;
   const size_t smem = (size_t)kb * a.npol * ld * sizeof(Cx<T>);
   int rc = set_smem(pfb_analysis_generic<T>, smem);

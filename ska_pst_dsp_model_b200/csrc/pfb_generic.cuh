@@ -65,16 +65,37 @@ __global__ void __launch_bounds__(256) pfb_analysis_generic(const AnalysisArgs a
     const int j = (e / npol) % N;
     const int kk = e / (npol * N);
     const long long t0 = a.start0 + (k0 + kk) * (long long)a.S;
-    T accx = 0, accy = 0;
-    for (int m = 0; m < a.P; ++m) {
-      const long long t = t0 + j + (long long)m * N;
-      if (t >= 0 && t < a.n_dat) {
-        const Cx<T> v = ldg_cx<T>(x + t * a.in_pitch + pol);
-        const T c = __ldg(f + j + m * N);
-        accx += c * v.x;
-        accy += c * v.y;
+    // taps whose sample lies inside the resident stream: m in [m_lo, m_hi); four independent chains
+    const long long tj = t0 + j;
+    long long m_lo = tj >= 0 ? 0 : (-tj + N - 1) / N;
+    long long m_hi = tj < a.n_dat ? (a.n_dat - tj + N - 1) / N : 0;
+    if (m_hi > a.P) m_hi = a.P;
+    if (m_lo > m_hi) m_lo = m_hi;
+    T ax[4] = {0, 0, 0, 0}, ay[4] = {0, 0, 0, 0};
+    const Cx<T>* __restrict__ xp = x + (tj + m_lo * N) * a.in_pitch + pol;
+    const T* __restrict__ fp = f + j + m_lo * N;
+    const long long xs = (long long)N * a.in_pitch;
+    int m = (int)m_lo;
+    for (; m + 4 <= (int)m_hi; m += 4) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const Cx<T> v = ldg_cx<T>(xp + u * xs);
+        const T c = __ldg(fp + u * N);
+        ax[u] += c * v.x;
+        ay[u] += c * v.y;
       }
+      xp += 4 * xs;
+      fp += 4 * N;
     }
+    for (; m < (int)m_hi; ++m) {
+      const Cx<T> v = ldg_cx<T>(xp);
+      const T c = __ldg(fp);
+      ax[0] += c * v.x;
+      ay[0] += c * v.y;
+      xp += xs;
+      fp += N;
+    }
+    const T accx = (ax[0] + ax[1]) + (ax[2] + ax[3]), accy = (ay[0] + ay[1]) + (ay[2] + ay[3]);
     const int slot = pmod(a.phase0 + t0 + j, N);
     s[(size_t)(kk * npol + pol) * ld + padi<T>(slot)] = mk<T>(accx, accy);
   }
