@@ -61,6 +61,37 @@ if "--skip-mid" not in sys.argv:
                    "analysis_Msamples_s": 2 * n / ms_a / 1e3, "round_trip_Msamples_s": 2 * n / (ms_a + ms_i) / 1e3,
                    "nblocks": int(chm.shape[0]), "kernels": "pfb_fir_phases + pfb_rowfft4096 (analysis), pfb_rowfft4096 + generic resample (inversion)"}
     del xm, chm, ana, inv
+# two-stage (Low scale as in test_sgcht options 4-8): 256 coarse x 256 fine channels, 4/3 both
+# stages, stage 2 and its inversion as ONE batched launch over all coarse channels
+from ska_pst_dsp_model_b200.filterbank import TwoStageFilterBank, TwoStageInverseFilterBank
+n2 = 1 << 23
+x2 = torch.view_as_complex(torch.randn((n2, 1, 2), device="cuda"))
+cfg = dict(filt_coeff=h, n_chan=256, os_factor="4/3")
+_tsf = TwoStageFilterBank(cfg, critical=False)
+
+
+def tsf():
+    for fb in (_tsf.stage1, _tsf.stage2):                     # same input every call: no carried tail
+        fb.buffered_samples, fb.input_buffer = 0, None
+    return _tsf.execute(x2)
+
+
+fine = tsf()
+icfg = dict(filt_coeff=h, n_fft=128, overlap=16, os_factor="4/3", temporal_taper="tukey")
+_tsi = TwoStageInverseFilterBank(icfg, nch2=256, stage2_nchan=256, combine=1)
+
+
+def tsi():
+    _tsi.buffered_samples, _tsi.input_buffer = 0, None       # same input every call: no carried tail
+    return _tsi.execute(fine)
+ms_f, ms_b = timeit(tsf, 3), timeit(tsi, 3)
+res["two_stage_low"] = {"shape": "2^23 x 1 pol -> 256 coarse x 256 fine channels (4/3 x 4/3, PST taps), inversion of stage 2 "
+                                 "(Nf=128, ov=16) for all coarse channels in one batched launch",
+                        "analysis_ms": ms_f, "stage2_inversion_ms": ms_b, "fine_shape": list(fine.shape),
+                        "analysis_Msamples_s": n2 / ms_f / 1e3,
+                        "kernels": "stage 1: pfb_analysis_low<1>; stage 2: generic batched analysis; inversion: "
+                                   "generic channel IDFT + pfb_resample_low (batched columns)"}
+del x2, fine
 # cfg5: batched purity sweep
 nvec = int(os.environ.get("NVEC", "512"))
 bp = BatchPurity("4/3", 256, 48, "tukey", True, 256, h, 3, vectors_per_batch=32)
