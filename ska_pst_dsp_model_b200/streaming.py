@@ -19,7 +19,7 @@ from .sharding import plan_time_shards
 
 class HostRoundTrip:
     def __init__(self, n_dat, nchan, os_factor, taps, input_fft_length, input_overlap, temporal_taper="tukey",
-                 deripple=True, npol=2, nseg=16, dtype=None, device=None, k_total=None, use_graph=True):
+                 deripple=True, npol=2, nseg=16, dtype=None, device=None, k_total=None, use_graph=True, nbuf=3):
         import torch
         from . import ops
         self.torch = torch
@@ -44,9 +44,10 @@ class HostRoundTrip:
         mx_in = max(s.need_n for s in self.segs)
         mx_fine = max(s.fine_n for s in self.segs)
         mx_out = max(s.out_n for s in self.segs)
-        self.din = [torch.empty((mx_in, npol), dtype=dtype, device=dev) for _ in range(2)]
-        self.dchan = [torch.empty((mx_fine, nchan, npol), dtype=dtype, device=dev) for _ in range(2)]
-        self.dout = [torch.empty((mx_out, npol), dtype=dtype, device=dev) for _ in range(2)]
+        self.nbuf = max(2, int(nbuf))                 # device buffers per stage: copies run ahead of / behind the kernels
+        self.din = [torch.empty((mx_in, npol), dtype=dtype, device=dev) for _ in range(self.nbuf)]
+        self.dchan = [torch.empty((mx_fine, nchan, npol), dtype=dtype, device=dev) for _ in range(self.nbuf)]
+        self.dout = [torch.empty((mx_out, npol), dtype=dtype, device=dev) for _ in range(self.nbuf)]
         self.s_in, self.s_cmp, self.s_out = (torch.cuda.Stream(dev) for _ in range(3))
         self.use_graph = use_graph
         self._graphs = {}         # (x.data_ptr, y.data_ptr) -> captured step
@@ -80,10 +81,10 @@ class HostRoundTrip:
         cur = torch.cuda.current_stream(self.device)
         for s in (self.s_in, self.s_cmp, self.s_out):
             s.wait_stream(cur)
-        ev_cmp = [None, None]     # compute finished reading din[slot] / writing dout[slot]
-        ev_out = [None, None]     # D2H finished reading dout[slot]
+        ev_cmp = [None] * self.nbuf     # compute finished reading din[slot] / writing dout[slot]
+        ev_out = [None] * self.nbuf     # D2H finished reading dout[slot]
         for g, sg in enumerate(self.segs):
-            slot = g & 1
+            slot = g % self.nbuf
             with torch.cuda.stream(self.s_in):
                 if ev_cmp[slot] is not None:
                     self.s_in.wait_event(ev_cmp[slot])
