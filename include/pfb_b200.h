@@ -124,6 +124,12 @@ int pfb_generate_test_vector(int kind, void* out_dev, long long n, int npol, int
  * two polarisation slots of one [n][2] stream, so that a pair runs through the dual-pol kernels in one pass */
 int pfb_generate_test_vector_strided(int kind, void* out_dev, long long n, long long stride, int dtype,
                                      double p0, double p1, double p2, void* stream);
+/* nvec vectors in one launch, parameters (p0, p1, p2 per vector) read from device memory so that a captured CUDA
+ * graph of a whole batch can be replayed with new parameters: vector i is written to
+ * out[(i / group) * group_stride + (i % group) + t * group], i.e. `group` vectors interleaved sample by sample
+ * (group = 2: the two polarisation slots of one [n][2] stream). */
+int pfb_generate_test_vectors(int kind, void* out_dev, long long n, int nvec, int group, long long group_stride,
+                              int dtype, const double* params_dev, void* stream);
 /* args_dev: device array of nvec records {const void* a; const void* b; long long n, stride_a, stride_b;
  * double scale_b; double* out;} (56 bytes each).  For every record one CTA reduces the series b (and the
  * reference a, may be NULL) and writes out[0..7] = sum|b-a|, max|b-a|, sum|b|^2, largest |b|^2,

@@ -965,6 +965,24 @@ int pfb_generate_test_vector_strided(int kind, void* out_dev, long long n, long 
   return generate_run(kind, out_dev, n, 1, stride, dtype, p0, p1, p2, stream);
 }
 
+int pfb_generate_test_vectors(int kind, void* out_dev, long long n, int nvec, int group, long long group_stride, int dtype,
+                              const double* params_dev, void* stream) {
+  if (!out_dev || !params_dev || n < 0 || nvec < 0 || group < 1 || (kind != 0 && kind != 1))
+    return fail(PFB_ERR_ARG, "pfb_generate_test_vectors: bad argument");
+  if (n == 0 || nvec == 0) return PFB_OK;
+  if (nvec > 65535) return fail(PFB_ERR_ARG, "pfb_generate_test_vectors: at most 65535 vectors per call");
+  GenBatchArgs a;
+  a.out = out_dev; a.n = n; a.group = group; a.group_stride = group_stride; a.kind = kind; a.params = params_dev;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  long long gx = (n + 255) / 256;
+  if (gx > 148 * 4) gx = 148 * 4;
+  const dim3 grid((unsigned)gx, (unsigned)nvec);
+  if (dtype == PFB_DTYPE_C64) pfb_generate_batch_kernel<float><<<grid, 256, 0, st>>>(a);
+  else if (dtype == PFB_DTYPE_C128) pfb_generate_batch_kernel<double><<<grid, 256, 0, st>>>(a);
+  else return fail(PFB_ERR_ARG, "dtype must be 0 (c64) or 1 (c128)");
+  return check_launch("pfb_generate_batch_kernel");
+}
+
 int pfb_purity_metrics(const void* args_dev, int nvec, int dtype, void* stream) {
   if (!args_dev || nvec < 0) return fail(PFB_ERR_ARG, "pfb_purity_metrics: bad argument");
   if (nvec == 0) return PFB_OK;

@@ -37,6 +37,39 @@ __global__ void __launch_bounds__(256) pfb_generate_kernel(const GenArgs a) {
   }
 }
 
+// many vectors in one launch: blockIdx.y = vector; parameters come from a device array so that a captured
+// CUDA graph of a whole batch can be replayed with new parameters
+struct GenBatchArgs {
+  void* out;
+  long long n;
+  long long group_stride;   // elements between consecutive groups of `group` interleaved vectors
+  int group;                // vectors interleaved sample by sample (2: the polarisation slots of one stream)
+  int kind;
+  const double* params;     // [nvec][3]
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) pfb_generate_batch_kernel(const GenBatchArgs a) {
+  const int v = blockIdx.y;
+  const double p0 = a.params[3 * v], p1 = a.params[3 * v + 1], p2 = a.params[3 * v + 2];
+  Cx<T>* out = reinterpret_cast<Cx<T>*>(a.out) + (long long)(v / a.group) * a.group_stride + (v % a.group);
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < a.n; t += (long long)gridDim.x * blockDim.x) {
+    Cx<T> val = mk<T>((T)0, (T)0);
+    if (a.kind == 0) {
+      const long long o = (long long)p0, w = (long long)p1;
+      if (t >= o && t < o + w) val.x = (T)1;
+    } else {
+      const double cyc = (p0 + p2) * (double)t / (double)a.n;
+      const double ang = 2.0 * 3.14159265358979323846 * (cyc - floor(cyc)) + p1;
+      double sn, cs;
+      sincos(ang, &sn, &cs);
+      val.x = (T)cs;
+      val.y = (T)sn;
+    }
+    out[t * a.group] = val;
+  }
+}
+
 struct MetricsArgs {
   const void* a;        // reference series (may be null), complex, element stride `stride`
   const void* b;        // series under test

@@ -22,6 +22,7 @@ EXPORTS = [
     "pfb_inverse_execute_stage", "pfb_inverse_set_profiling", "pfb_inverse_get_profile",
     "pfb_inverse_set_spectral_taper", "pfb_generate_test_vector", "pfb_purity_metrics",
     "pfb_analysis_execute_batched", "pfb_inverse_execute_batched", "pfb_generate_test_vector_strided",
+    "pfb_generate_test_vectors",
 ]
 
 PFB_DTYPE_C64, PFB_DTYPE_C128 = 0, 1
@@ -66,6 +67,7 @@ def _load():
     c_d = ctypes.c_double
     lib.pfb_generate_test_vector.argtypes = [c_int, c_vp, c_ll, c_int, c_int, c_d, c_d, c_d, c_vp]
     lib.pfb_generate_test_vector_strided.argtypes = [c_int, c_vp, c_ll, c_ll, c_int, c_d, c_d, c_d, c_vp]
+    lib.pfb_generate_test_vectors.argtypes = [c_int, c_vp, c_ll, c_int, c_int, c_ll, c_int, c_vp, c_vp]
     lib.pfb_purity_metrics.argtypes = [c_vp, c_int, c_int, c_vp]
     lib.pfb_analysis_execute_batched.argtypes = [c_vp, c_vp, c_vp, c_int, c_ll, c_int, c_int, c_vp]
     lib.pfb_inverse_execute_batched.argtypes = [c_vp, c_vp, c_vp, c_int, c_int, c_ll, c_vp]
