@@ -442,7 +442,7 @@ def main():
     ap.add_argument("--log2-samples", type=int, default=24, help="samples per pol per GPU (default 2^24)")
     ap.add_argument("--cpu-log2-samples", type=int, default=22, help="bounded CPU sample per pol")
     ap.add_argument("--e2e-steps", type=int, default=5)
-    ap.add_argument("--e2e-segments", type=int, default=16)
+    ap.add_argument("--e2e-segments", type=int, default=8, help="base segment count of the host round trip (ramped head and tail add a few)")
     ap.add_argument("--scratch-mib", type=int, default=0, help="override the inversion scratch cap (default 1 GiB: one chunk)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

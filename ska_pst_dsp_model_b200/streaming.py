@@ -3,7 +3,9 @@ the D2H copy of successive time segments overlapped on three CUDA streams.
 
 The whole step (every copy and kernel of every segment, with its cross-stream dependencies) is
 captured once per pair of host buffers into a CUDA graph and replayed with a single launch, so the
-host cost per segment does not limit how finely the stream can be cut.
+host cost per segment does not limit how finely the stream can be cut.  Segment sizes ramp up at the head
+and down at the tail (the first H2D copy and the last D2H copy overlap nothing), and every stage has three
+device buffers so the copy engines run ahead of / behind the kernels.
 
 This is the executor behind the end-to-end number (`e2e` in bench.py) and the
 file-level operators for large inputs: the reference moves data between stages
@@ -19,7 +21,7 @@ from .sharding import plan_time_shards
 
 class HostRoundTrip:
     def __init__(self, n_dat, nchan, os_factor, taps, input_fft_length, input_overlap, temporal_taper="tukey",
-                 deripple=True, npol=2, nseg=16, dtype=None, device=None, k_total=None, use_graph=True, nbuf=3):
+                 deripple=True, npol=2, nseg=8, dtype=None, device=None, k_total=None, use_graph=True, nbuf=3, ramp=True):
         import torch
         from . import ops
         self.torch = torch
@@ -31,15 +33,17 @@ class HostRoundTrip:
         dev = self.analysis.device
         self.device = dev
         nseg = max(1, nseg)
+        fine = 4 * nseg                              # fine cuts, merged below into a ramped profile
         while True:
             try:
-                self.segs = plan_time_shards(n_dat, nseg, nchan, os_factor, len(taps), input_fft_length,
-                                             input_overlap, k_total=k_total)
+                cuts = plan_time_shards(n_dat, fine, nchan, os_factor, len(taps), input_fft_length,
+                                        input_overlap, k_total=k_total)
                 break
             except ValueError:
-                if nseg == 1:
+                if fine == 1:
                     raise
-                nseg //= 2
+                fine //= 2
+        self.segs = self._ramp(cuts, nseg) if ramp else self._ramp(cuts, nseg, flat=True)
         self.n_out = self.segs[-1].out0 + self.segs[-1].out_n
         mx_in = max(s.need_n for s in self.segs)
         mx_fine = max(s.fine_n for s in self.segs)
@@ -52,6 +56,37 @@ class HostRoundTrip:
         self.use_graph = use_graph
         self._graphs = {}         # (x.data_ptr, y.data_ptr) -> captured step
         self._warm = False
+
+    @staticmethod
+    def _ramp(cuts, nseg, flat=False):
+        """Merge the fine cuts into ~nseg segments whose sizes ramp up from one fine cut at the head and down to one at
+        the tail: the first H2D copy and the last D2H copy, which nothing overlaps, stay short."""
+        from types import SimpleNamespace
+        n = len(cuts)
+        if flat or n <= 4:
+            per = max(1, n // max(1, min(nseg, n)))
+            sizes = [per] * (n // per)
+            sizes[-1] += n - sum(sizes)
+        else:
+            big = max(1, -(-n // nseg))
+            head, sz = [], 1
+            while sz < big and 2 * (sum(head) + sz) < n // 2:
+                head.append(sz)
+                sz *= 2
+            mid = n - 2 * sum(head)
+            body = [big] * (mid // big)
+            if mid % big:
+                body.append(mid % big)
+            sizes = head + body + head[::-1]
+        segs, i = [], 0
+        for sz in sizes:
+            a, b = cuts[i], cuts[i + sz - 1]
+            segs.append(SimpleNamespace(need0=a.need0, need_n=b.need0 + b.need_n - a.need0,
+                                        fine0=a.fine0, fine_n=b.fine0 + b.fine_n - a.fine0,
+                                        out0=a.out0, out_n=b.out0 + b.out_n - a.out0))
+            i += sz
+        assert i == n
+        return segs
 
     def run(self, x_host, y_host):
         """x_host: pinned [n_dat, npol]; y_host: pinned [n_out, npol]. Returns after the work is
