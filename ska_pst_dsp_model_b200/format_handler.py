@@ -30,6 +30,15 @@ def _tdtype(np_dtype):
     return torch.complex128 if np.dtype(np_dtype) == np.complex128 else torch.complex64
 
 
+def _stream_it(path) -> bool:
+    """Files whose payload exceeds PFB_STREAM_BYTES (default 1 GiB) go through the streaming operators."""
+    try:
+        limit = int(os.environ.get("PFB_STREAM_BYTES", str(1 << 30)))
+        return os.path.getsize(path) > limit
+    except OSError:
+        return False
+
+
 def _fmt_num(v: float) -> str:
     s = repr(float(v))
     return s[:-2] if s.endswith(".0") else s
@@ -69,6 +78,12 @@ class PSRFormatChannelizer:
         return out.cpu().numpy()
 
     def __call__(self, input_data_file, output_dir="./", output_file_name=None):
+        if input_data_file.data is None and _stream_it(input_data_file.file_path) and \
+                self.analysis_function != "polyphase_analysis_padded":
+            # large file not yet in memory: stream it piecewise through pinned buffers (file_streaming.py);
+            # the returned object holds the header, .load_data() reads the payload
+            from .file_streaming import stream_channelize
+            return stream_channelize(self, input_data_file.file_path, output_dir, output_file_name)
         if input_data_file.data is None:
             input_data_file.load_data()
         out = self.channelize_array(input_data_file.data)
@@ -125,6 +140,9 @@ class PSRFormatSynthesizer:
         return out.cpu().numpy()[:, None, :]
 
     def __call__(self, input_data_file, output_dir="./", output_file_name=None):
+        if input_data_file.data is None and _stream_it(input_data_file.file_path):
+            from .file_streaming import stream_synthesize
+            return stream_synthesize(self, input_data_file.file_path, output_dir, output_file_name)
         if input_data_file.data is None:
             input_data_file.load_data()
         hdr = input_data_file.header

@@ -92,6 +92,29 @@ res["two_stage_low"] = {"shape": "2^23 x 1 pol -> 256 coarse x 256 fine channels
                         "kernels": "stage 1: pfb_analysis_low<1>; stage 2: generic batched analysis; inversion: "
                                    "generic channel IDFT + pfb_resample_low (batched columns)"}
 del x2, fine
+# file -> file through the streaming operators: 2^24 x 2 pol complex64 DADA file (256 MiB) channelized
+# to 341 MiB and inverted to 255 MiB, pieces read into pinned memory / written by I/O threads
+import tempfile
+from ska_pst_dsp_model_b200.file_streaming import stream_channelize, stream_synthesize
+from ska_pst_dsp_model_b200.format_handler import PSRFormatChannelizer, PSRFormatSynthesizer
+from ska_pst_dsp_model_b200.formats import DADAFile
+from ska_pst_dsp_model_b200.fft_windows import tukey_window
+with tempfile.TemporaryDirectory() as td:
+    nf = 1 << 24
+    xf = (np.random.default_rng(0).standard_normal((nf, 1, 2, 2)).astype(np.float32)).view(np.complex64)[..., 0]
+    DADAFile(os.path.join(td, "in.dump"), data=xf).dump_data()
+    chz = PSRFormatChannelizer("4/3", 256, h)
+    syn = PSRFormatSynthesizer(48, tukey_window(256, 48), 256, apply_deripple=True)
+    stream_channelize(chz, os.path.join(td, "in.dump"), td, "w.dump", blocks_per_piece=4096)      # warm-up (plans, page cache)
+    t0 = time.time()
+    ch_f = stream_channelize(chz, os.path.join(td, "in.dump"), td, "ch.dump", blocks_per_piece=4096)
+    t1 = time.time()
+    stream_synthesize(syn, ch_f.file_path, td, "syn.dump", blocks_per_piece=32)
+    t2 = time.time()
+    res["file_streaming"] = {"shape": "2^24 x 2 pol complex64 DADA file -> channelized file -> inverted file (tmpfs/disk of the box)",
+                             "channelize_s": t1 - t0, "synthesize_s": t2 - t1,
+                             "channelize_Msamples_s": nf / (t1 - t0) / 1e6, "synthesize_Msamples_s": nf / (t2 - t1) / 1e6}
+    del xf
 # cfg5: batched purity sweep
 nvec = int(os.environ.get("NVEC", "512"))
 bp = BatchPurity("4/3", 256, 48, "tukey", True, 256, h, 3, vectors_per_batch=32)
