@@ -1,7 +1,10 @@
 // Shape-specialised fast kernels for the SKA-Low PST shape (fp32):
-//   K1  pfb_analysis_low  : 256 channels, OS 4/3 (step 192), 12 taps/arm (3072-tap filter)
-//   K2  pfb_chan_idft_low : 256-point inverse DFT across channels
-//   K3  pfb_resample_low  : Nf=256 -> FN_width=192 overlap-save resampling per column
+//   K1  pfb_analysis_low      : 256 channels, OS 4/3 (step 192), 12 taps/arm (3072-tap filter)
+//   K2  pfb_chan_idft_low_*   : 256-point inverse DFT across channels (TMA-fed; optionally writes the grouped,
+//                               bank-swizzled scratch layout that K3 streams)
+//   K3  pfb_resample_low_ws   : Nf=256 -> FN_width=192 overlap-save resampling per column, warp-autonomous and
+//                               TMA-streamed (dual-pol, ov=48); pfb_resample_low is the block-synchronous form
+//                               for single-pol / critically sampled / batched plans
 // Selected by the plan when the shape matches; anything else runs pfb_generic.cuh.
 //
 // Design notes (DESIGN.md has the derivations):
@@ -13,13 +16,15 @@
 //    in 16 complex MACs; the window rotation is resolved statically by unrolling 16 blocks.
 //    The 4 arms a thread produces are exactly the inputs of one radix-4 DIF butterfly of
 //    the 256-point FFT, and the oversampling phase rotation (a multiple of 64 slots) is a
-//    static renaming of those 4 registers.  The remaining 64-point FFTs run one per thread,
-//    entirely in registers, after one exchange through shared memory.
+//    static renaming of those 4 registers.  The remaining 64-point FFTs run one per thread
+//    after one exchange through shared memory.
 //  * input is streamed by the TMA bulk-copy engine (cp.async.bulk + mbarrier) into a
 //    3-stage shared-memory ring; outputs go straight from registers to global memory in
 //    fully used 32-byte sectors.
 //  * K2/K3 split the 256-point FFT 16 x 16 (and the 192-point inverse 12 x 16) over 16
-//    lanes per transform with in-register radix-16/12 butterflies and compile-time twiddles.
+//    lanes per transform with in-register radix-16/12 butterflies and compile-time twiddles;
+//    in K2 and the warp-autonomous K3 the 16 lanes share a warp, so the passes exchange data
+//    with __syncwarp() only.
 #pragma once
 #include <cuda.h>
 #include <cstdlib>
