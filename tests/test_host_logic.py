@@ -161,3 +161,25 @@ def test_purity_driver_parameters():
     assert t.total_sample_shift == 36 * 256 + 1535
     assert list(t.time_domain_args["offset"]) == list(np.linspace(1, 147456, 5).astype(int))
     assert list(t.freq_domain_args["frequency"]) == list(np.linspace(1, 49152, 5).astype(int) * 3)
+
+
+def test_host_round_trip_ramped_segments_tile_the_stream():
+    """streaming.HostRoundTrip._ramp merges the fine time cuts into segments that ramp up at the head and down at
+    the tail; they must tile inputs, fine blocks and outputs exactly like the cuts they were merged from."""
+    from ska_pst_dsp_model_b200.sharding import plan_time_shards
+    from ska_pst_dsp_model_b200.streaming import HostRoundTrip
+    n = 1 << 22
+    cuts = plan_time_shards(n, 32, 256, "4/3", 3072, 256, 48)
+    for flat in (False, True):
+        segs = HostRoundTrip._ramp(cuts, 8, flat=flat)
+        assert segs[0].out0 == 0 and segs[0].need0 == cuts[0].need0 and segs[0].fine0 == cuts[0].fine0
+        for a, b in zip(segs, segs[1:]):
+            assert a.out0 + a.out_n == b.out0
+            assert b.need0 < a.need0 + a.need_n              # the FIR history / overlap-save overlap is re-read
+        last = segs[-1]
+        assert last.out0 + last.out_n == cuts[-1].out0 + cuts[-1].out_n
+        assert last.need0 + last.need_n == cuts[-1].need0 + cuts[-1].need_n
+        assert last.fine0 + last.fine_n == cuts[-1].fine0 + cuts[-1].fine_n
+        assert sum(s.out_n for s in segs) == sum(c.out_n for c in cuts)
+    ramped = HostRoundTrip._ramp(cuts, 8)
+    assert ramped[0].out_n < ramped[len(ramped) // 2].out_n and ramped[-1].out_n < ramped[len(ramped) // 2].out_n
