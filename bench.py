@@ -63,32 +63,41 @@ def comb_params():
     return amps, freqs
 
 
-def synth_numpy(t0, n, npol):
+def comb_period_table():
+    """The comb's 32 tones sit 1/32 cycles/sample apart, so x[t] = exp(2 pi i f0 t) * P[t mod 32] / 32 with
+    P[m] = sum_k a_k exp(2 pi i k m / 32): one complex exponential per sample instead of 32."""
     import numpy as np
     amps, freqs = comb_params()
-    t = np.arange(t0, t0 + n, dtype=np.float64)
-    x = np.zeros(n, dtype=np.complex128)
-    for a, f in zip(amps, freqs):
-        x += a * np.exp(2j * np.pi * np.mod(f * t, 1.0))
-    x /= 32.0
-    x[(np.arange(t0, t0 + n) % 30720) == 0] += 1.0
-    return np.repeat(x.astype(np.complex64)[:, None], npol, axis=1)
+    m = np.arange(32)
+    P = (amps[None, :] * np.exp(2j * np.pi * ((np.arange(32)[None, :] * m[:, None]) % 32) / 32.0)).sum(axis=1)
+    return float(freqs[0]), P / 32.0
+
+
+def synth_numpy(t0, n, npol):
+    import numpy as np
+    f0, P = comb_period_table()
+    out = np.empty((n, npol), dtype=np.complex64)
+    chunk = 1 << 21
+    for c0 in range(0, n, chunk):
+        m = min(chunk, n - c0)
+        ti = np.arange(t0 + c0, t0 + c0 + m, dtype=np.int64)
+        x = np.exp(2j * np.pi * np.mod(f0 * ti.astype(np.float64), 1.0)) * P[ti % 32]
+        x[(ti % 30720) == 0] += 1.0
+        out[c0:c0 + m] = x.astype(np.complex64)[:, None]
+    return out
 
 
 def synth_torch(t0, n, npol, device):
     import torch
-    amps, freqs = comb_params()
+    f0, P = comb_period_table()
+    Pd = torch.from_numpy(P).to(device)
     out = torch.empty((n, npol), dtype=torch.complex64, device=device)
-    chunk = 1 << 21
+    chunk = 1 << 22
     for c0 in range(0, n, chunk):
         m = min(chunk, n - c0)
-        t = torch.arange(t0 + c0, t0 + c0 + m, dtype=torch.float64, device=device)
-        acc = torch.zeros(m, dtype=torch.complex128, device=device)
-        for a, f in zip(amps, freqs):
-            ph = torch.remainder(t * float(f), 1.0) * (2 * torch.pi)
-            acc += float(a) * torch.polar(torch.ones_like(ph), ph)
-        acc /= 32.0
         ti = torch.arange(t0 + c0, t0 + c0 + m, dtype=torch.int64, device=device)
+        ph = torch.remainder(ti.to(torch.float64) * f0, 1.0) * (2 * torch.pi)
+        acc = torch.polar(torch.ones_like(ph), ph) * Pd[ti % 32]
         acc[(ti % 30720) == 0] += 1.0
         out[c0:c0 + m] = acc.to(torch.complex64)[:, None]
     return out
@@ -98,6 +107,31 @@ def synth_torch(t0, n, npol, device):
 # CPU reference arm: the numpy oracle (port of the Matlab model) on all host cores
 # --------------------------------------------------------------------------
 _CPU = {}
+_THREAD_VARS = ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS", "NUMEXPR_NUM_THREADS", "VECLIB_MAXIMUM_THREADS")
+
+
+def host_cores():
+    """Cores this process may run on (the cgroup / affinity mask, not the machine's count)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def _pin_blas_threads():
+    """One BLAS/OpenMP thread per worker process: the arm parallelises over processes, and unpinned BLAS pools
+    oversubscribe the cores (round 1: 3.3 vs 15.6 Msamples/s on the same 8 cores)."""
+    for k in _THREAD_VARS:
+        os.environ[k] = "1"
+
+
+def _cpu_init():
+    _pin_blas_threads()
+    try:
+        from threadpoolctl import threadpool_limits
+        _CPU["limits"] = threadpool_limits(limits=1)
+    except Exception:           # noqa: BLE001
+        pass
 
 
 def _cpu_worker(job):
@@ -137,17 +171,21 @@ def cpu_round_trip_setup(log2n, workers):
     # the reference's nblocks = floor((n_dat - fl)/step) (polyphase_analysis.m:62) is one
     # short of what fits, so hand each segment one extra step of input
     jobs = [(s.need0, s.need_n + 192, s.out0, s.out_n) for s in shards]
-    pool = mp.get_context("fork").Pool(workers)
+    _pin_blas_threads()
+    pool = mp.get_context("fork").Pool(workers, initializer=_cpu_init)
     return pool, jobs, n * NPOL
 
 
 def run_reference(args):
-    """`--impl reference`: the oracle port on the host cores, bounded sample per step."""
+    """`--impl reference`: the oracle port on the host cores.  One step = the whole per-GPU
+    configuration (2^24 samples/pol x 2 pol) unless --cpu-log2-samples bounds it; at N > 1 the stream of the
+    B200 arm is N times longer, the CPU step stays one GPU's share (a bounded sample: the metric is a rate)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    workers = min(os.cpu_count() or 1, 64)
-    log2n = args.cpu_log2_samples
+    _pin_blas_threads()
+    workers = min(host_cores(), 64)
+    log2n = args.cpu_log2_samples if args.cpu_log2_samples else args.log2_samples
     pool, jobs, samples = cpu_round_trip_setup(log2n, workers)
     for _ in range(args.warmup):
         pool.map(_cpu_worker, jobs)
@@ -157,16 +195,22 @@ def run_reference(args):
     dt = (time.perf_counter() - t0) / args.steps
     pool.close()
     value = samples / dt / 1e6
-    sample = f"first 2^{log2n} samples/pol x {NPOL} pol of the same synthetic stream per step, {len(jobs)} time segments"
+    whole = log2n == args.log2_samples
+    sample = (f"{'the whole' if whole else 'first'} 2^{log2n} samples/pol x {NPOL} pol of the same synthetic stream per step "
+              f"({'= one GPU share of the config' if whole else 'bounded prefix'}), {len(jobs)} time segments over "
+              f"{workers} processes, 1 BLAS/OpenMP thread each")
+    cfg = workload_config(args.log2_samples, args.gpus)
+    cfg["cpu_step"] = sample
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args.log2_samples, args.gpus),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "port", "sample": sample},
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "io_dtype": "complex64", "data": "synthetic",
+        "config": cfg,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "port", "sample": sample,
+                         "threads_per_process": 1, "host_cpu_count": os.cpu_count()},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "note": "numpy port of the reference's Matlab model (oracle/pfb_oracle.py); the reference itself cannot "
-                "run here (Matlab / un-vendored pfb package)",
+        "note": "numpy port of the reference's Matlab model (oracle/pfb_oracle.py), fp64 arithmetic as the Matlab scratch "
+                "arrays (polyphase_synthesis.m:152-154); the reference itself cannot run here (Matlab / un-vendored pfb package)",
     }
     print(json.dumps(line), flush=True)
     return 0
@@ -337,6 +381,33 @@ def run_b200(args):
     ms_analysis = sum(e[0].elapsed_time(e[1]) for e in ev) / K
     ms_inverse = sum(e[1].elapsed_time(e[2]) for e in ev) / K
 
+    # ---- sustained: the same step back to back for >= --min-seconds (clocks / power under a long run) ----
+    sustained = None
+    if args.min_seconds > 0:
+        ks = max(K, int(args.min_seconds * 1e3 / ms_step) + 1)
+        samp2 = ClockSampler(local_rank)
+        if rank == 0:
+            samp2.start()
+        barrier()
+        tb = time.perf_counter()
+        s1, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s1.record()
+        for _ in range(ks):
+            rt.run_analysis()
+            rt.inverse(rt.chan, out=rt.out)
+        e1.record()
+        barrier()
+        te = time.perf_counter()
+        ms_s = s1.elapsed_time(e1) / ks
+        ts = torch.tensor([ms_s], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+        ms_s = float(ts.item())
+        launches += 0   # (not part of the K-step claim)
+        sustained = {"steps": ks, "seconds": ms_s * ks * 1e-3, "ms_per_step": ms_s,
+                     "value": total_samples / (ms_s * 1e-3) / 1e6, "unit": UNIT,
+                     "vs_burst": ms_step / ms_s, "clocks": samp2.stop(tb, te) if rank == 0 else None}
+
     # ---- per-kernel roofline (algorithmic bytes = the kernel's compulsory I/O) -
     cb = 8  # complex64
     bytes_analysis = (shard.need_n * NPOL + shard.fine_n * NCHAN * NPOL) * cb
@@ -359,9 +430,20 @@ def run_b200(args):
                 "frac": dk["frac"], "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": dk["bytes_per_step"] / dk["launches_per_step"],
                 "avg_launch_ms": dk["ms_per_step"] / dk["launches_per_step"]}
-    e2e_bytes = 16 * (1 + osf) * (samples_rank)       # round trip with materialised channels
-    pipeline = {"algorithmic_bytes_per_step": e2e_bytes, "gbs": e2e_bytes / (ms_step * 1e-3) / 1e9,
-                "frac": e2e_bytes / (ms_step * 1e-3) / 1e9 / peak, "ms_analysis": ms_analysis, "ms_inversion": ms_inverse}
+    # the round trip with the channelized data materialised moves 16(1+OS) B per input sample per pol
+    # (actual elements counted: the analysis reads need_n, the inversion writes out_n)
+    rt_bytes = bytes_analysis + (shard.fine_n * NCHAN * NPOL + shard.out_n * NPOL) * cb
+    pipeline = {"algorithmic_bytes_per_step": rt_bytes, "gbs": rt_bytes / (ms_step * 1e-3) / 1e9,
+                "frac": rt_bytes / (ms_step * 1e-3) / 1e9 / peak, "ms_analysis": ms_analysis, "ms_inversion": ms_inverse,
+                "frac_analysis": bytes_analysis / (ms_analysis * 1e-3) / 1e9 / peak,
+                "frac_inversion": (rt_bytes - bytes_analysis) / (ms_inverse * 1e-3) / 1e9 / peak,
+                "nominal_16_1plusOS_bytes": 16 * (1 + osf) * samples_rank}
+    roofline.update({"pipeline_frac": pipeline["frac"], "pipeline_achieved": pipeline["gbs"],
+                     "pipeline_algorithmic_bytes_per_step": rt_bytes,
+                     "peak_nominal": 8000.0, "frac_of_nominal": dk["gbs"] / 8000.0,
+                     "pipeline_frac_of_nominal": pipeline["gbs"] / 8000.0,
+                     "note": "frac = dominant kernel's own compulsory bytes / its CUDA-event time / measured copy peak; "
+                             "pipeline_frac = SURVEY 8(d) round-trip bytes (16(1+OS) B/sample) / step time / the same peak"})
 
     # ---- e2e: pinned host buffers through the public streaming operator ------
     # (H2D of the rank's samples incl. halo, kernels, D2H of the inverted series, overlapped
@@ -405,8 +487,9 @@ def run_b200(args):
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        workers = min(os.cpu_count() or 1, 64)
-        pool, jobs, samples = cpu_round_trip_setup(args.cpu_log2_samples, workers)
+        workers = min(host_cores(), 64)
+        clog2 = args.cpu_log2_samples or min(22, log2n)
+        pool, jobs, samples = cpu_round_trip_setup(clog2, workers)
         pool.map(_cpu_worker, jobs[: workers])               # warm the pool
         t0 = time.perf_counter()
         reps = 0
@@ -421,10 +504,20 @@ def run_b200(args):
         got = rt.out[:m].cpu().numpy()
         perr = float(np.abs(got - ref[:m]).max() / np.abs(ref[:m]).max())
         cpu_baseline = {"value": samples / dt / 1e6, "unit": UNIT, "cores": workers, "kind": "port",
-                        "sample": f"first 2^{args.cpu_log2_samples} samples/pol x {NPOL} pol of the same stream, "
-                                  f"{reps} repetitions, {len(jobs)} segments over {workers} processes",
+                        "sample": f"first 2^{clog2} samples/pol x {NPOL} pol of the same stream, "
+                                  f"{reps} repetitions, {len(jobs)} segments over {workers} processes, 1 BLAS thread each",
+                        "threads_per_process": 1, "host_cpu_count": os.cpu_count(),
                         "parity_vs_gpu_prefix": perr}
 
+    other = None
+    if rank == 0 and world == 1 and not args.no_other_configs:
+        del hrt, x_host, y_host
+        rt.out = rt.local = None
+        torch.cuda.empty_cache()
+        try:
+            other = measure_other_configs(dev, peak, cpu=not args.no_cpu_baseline)
+        except Exception as e:          # noqa: BLE001  (side measurements must not lose the bench line)
+            other = {"error": repr(e)}
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -435,10 +528,121 @@ def run_b200(args):
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "config": workload_config(log2n, world), "clocks": clocks, "e2e": e2e,
         "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline, "kernels": kernels,
-        "pipeline": pipeline, "round_trip_max_err": rt_err,
+        "pipeline": pipeline, "sustained": sustained, "round_trip_max_err": rt_err,
+        "other_configs": other,
     }
     print(json.dumps(line), flush=True)
     return 0
+
+
+# --------------------------------------------------------------------------
+# the other BASELINE configs, measured in the same run (parity-test cases, not the bench line)
+# --------------------------------------------------------------------------
+def _time_cuda(fn, reps):
+    import torch
+    fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def _cpu_cfg_worker(job):
+    """One independent stream per worker process through the oracle (analysis + inversion)."""
+    import numpy as np
+    from oracle import pfb_oracle as orc
+    kind, seed = job
+    c = _CPU["cfg"][kind]
+    rng = np.random.default_rng(seed)
+    if kind == "cfg1":
+        x = np.zeros((1, 1, c["n"]), dtype=np.complex128)
+        x[0, 0, int(0.11 * c["n"])] = 1.0
+        ch = orc.polyphase_analysis(x, c["taps"], 8, "8/7")
+        y = orc.polyphase_synthesis(ch, True, 256, "8/7", c["taps"], 1, 48, c["taper"])
+    else:
+        x = rng.standard_normal((1, 1, c["n"])) + 1j * rng.standard_normal((1, 1, c["n"]))
+        ch = orc.polyphase_analysis_padded(x, c["taps"], 4096, "8/7")
+        y = orc.polyphase_synthesis(ch, True, 512, "8/7", c["taps"], 1, 128, c["taper"])
+    return int(y.shape[2])
+
+
+def _cpu_cfg_rate(kind, cfg, workers):
+    """All-core CPU rate of the oracle on `kind`: every worker runs one independent stream of cfg['n'] samples."""
+    import multiprocessing as mp
+    _CPU.setdefault("cfg", {})[kind] = cfg
+    _pin_blas_threads()
+    pool = mp.get_context("fork").Pool(workers, initializer=_cpu_init)
+    t0 = time.perf_counter()
+    pool.map(_cpu_cfg_worker, [(kind, i) for i in range(workers)])
+    dt = time.perf_counter() - t0
+    pool.close()
+    return {"value": workers * cfg["n"] / dt / 1e6, "unit": UNIT, "cores": workers, "kind": "port", "threads_per_process": 1,
+            "sample": f"{workers} independent streams of {cfg['n']} samples x 1 pol, one per process, {dt:.1f} s"}
+
+
+def measure_other_configs(dev, peak, cpu=True):
+    """BASELINE configs[0] (cfg1), configs[2] (cfg3, SKA-Mid at 2^24 x 2 pol) and configs[4] (cfg5, purity sweep)
+    on this GPU, each with its own roofline figure and an all-core oracle rate on a bounded sample."""
+    import numpy as np
+    import torch
+    from oracle import pfb_oracle as orc
+    from ska_pst_dsp_model_b200 import ops
+    from ska_pst_dsp_model_b200.filters import design_pfb_fir_filter_two_stage, load_pst_taps
+    workers = min(host_cores(), 64)
+    res = {}
+    h = load_pst_taps(normalise=True)
+    cb = 8
+    # ---- cfg1: 8 channels, OS 8/7, 3072 taps (384 per arm: FMA-bound), 2^18 single-pol impulse -------------
+    n = 1 << 18
+    x = torch.zeros((n, 1), dtype=torch.complex64, device=dev)
+    x[int(0.11 * n)] = 1
+    ana = ops.AnalysisPlan(8, "8/7", h, device=dev)
+    inv = ops.InversePlan(8, "8/7", 256, 48, "tukey", deripple_taps=h, device=dev)
+    ch = ana(x)
+    y = inv(ch)
+    ms_a = _time_cuda(lambda: ana(x, out=ch), 20)
+    ms_i = _time_cuda(lambda: inv(ch, out=y), 20)
+    flop_a = (4.0 * 3072 / 7 + 5.0 * 8 * 3 / 7 + 6.0 * 8 / 7) * n            # SURVEY 8(d): 1759 flop/sample
+    by = (n + 2 * ch.numel() + y.numel()) * cb
+    res["cfg1"] = {"workload": "8 ch, OS 8/7, PST taps (384/arm), 2^18 x 1 pol impulse; inversion Nf=256 ov=48",
+                   "ms_analysis": ms_a, "ms_inversion": ms_i, "value": n / (ms_a + ms_i) / 1e3, "unit": UNIT,
+                   "analysis_Msamples_s": n / ms_a / 1e3,
+                   "roofline": {"bound": "fp32 FMA (analysis)", "achieved": flop_a / (ms_a * 1e-3) / 1e12, "peak": 74.0,
+                                "unit": "TFLOP/s", "frac": flop_a / (ms_a * 1e-3) / 1e12 / 74.0,
+                                "peak_source": "nominal fp32 FMA roof (SURVEY 7 hard part 2)",
+                                "hbm_frac_round_trip": by / ((ms_a + ms_i) * 1e-3) / 1e9 / peak}}
+    if cpu:
+        res["cfg1"]["cpu_baseline"] = _cpu_cfg_rate("cfg1", {"n": n, "taps": h, "taper": orc.window_tukey(256, 48)}, workers)
+    del x, ch, y, ana, inv
+    # ---- cfg3: SKA-Mid, 4096 ch, OS 8/7, 100 353-tap two-stage design, padded analysis, Nf=512 ov=128 ------
+    hm = design_pfb_fir_filter_two_stage(4096, 8, 7)
+    n = 1 << 24
+    g = torch.Generator(device=dev)
+    g.manual_seed(3)
+    xm = torch.view_as_complex(torch.randn((n, 2, 2), device=dev, generator=g))
+    ana = ops.AnalysisPlan(4096, "8/7", hm, "polyphase_analysis_padded", device=dev)
+    inv = ops.InversePlan(4096, "8/7", 512, 128, "tukey", deripple_taps=hm, device=dev)
+    chm = ana(xm)
+    ym = inv(chm)
+    ms_a = _time_cuda(lambda: ana(xm, out=chm), 5)
+    ms_i = _time_cuda(lambda: inv(chm, out=ym), 5)
+    by = (xm.numel() + 2 * chm.numel() + ym.numel()) * cb
+    res["cfg3"] = {"workload": f"SKA-Mid: 4096 ch, OS 8/7, {hm.size} taps (padded analysis), Nf=512 ov=128 tukey+deripple, "
+                               f"2 pol x 2^24 complex64", "nblocks": int(chm.shape[0]),
+                   "ms_analysis": ms_a, "ms_inversion": ms_i, "value": 2 * n / (ms_a + ms_i) / 1e3, "unit": UNIT,
+                   "roofline": {"bound": "hbm", "achieved": by / ((ms_a + ms_i) * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                                "frac": by / ((ms_a + ms_i) * 1e-3) / 1e9 / peak,
+                                "algorithmic_bytes": by, "what": "round trip, channelized data materialised (SURVEY 8d)"}}
+    if cpu:
+        res["cfg3"]["cpu_baseline"] = _cpu_cfg_rate("cfg3", {"n": 1 << 22, "taps": hm, "taper": orc.window_tukey(512, 128)},
+                                                    min(workers, 16))
+    del xm, chm, ym, ana, inv
+    torch.cuda.empty_cache()
+    return res
 
 
 def main():
@@ -448,7 +652,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--log2-samples", type=int, default=24, help="samples per pol per GPU (default 2^24)")
-    ap.add_argument("--cpu-log2-samples", type=int, default=22, help="bounded CPU sample per pol")
+    ap.add_argument("--cpu-log2-samples", type=int, default=0,
+                    help="CPU sample per pol (default: the whole per-GPU config for --impl reference, 2^22 for the cpu_baseline leg)")
+    ap.add_argument("--min-seconds", type=float, default=1.0, help="length of the extra sustained run (0 = skip)")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the cfg1 / cfg3 / cfg5 side measurements")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--e2e-segments", type=int, default=8, help="base segment count of the host round trip (ramped head and tail add a few)")
     ap.add_argument("--scratch-mib", type=int, default=0, help="override the inversion scratch cap (default 1 GiB: one chunk)")

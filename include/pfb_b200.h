@@ -101,6 +101,12 @@ int pfb_inverse_set_spectral_taper(pfb_inverse_plan* plan, const double* taper, 
 /* bytes of scratch between the two inversion kernels (default 1 GiB: the whole stream in one chunk up to ~2^25
  * samples/pol at the SKA-Low shape; longer streams are processed in chunks of whole overlap-save blocks) */
 int pfb_inverse_set_scratch_bytes(pfb_inverse_plan* plan, long long bytes);
+/* Sizes the plan's scratch for streams of up to n_dat fine-channel samples (ngroups = 1 unless the batched call is
+ * used) WITHOUT launching anything.  A plan is single-stream and not thread-safe; its scratch grows on demand with
+ * cudaFree + cudaMalloc, which is illegal during stream capture and would leave an earlier captured graph with a
+ * stale pointer - reserve first, then capture.  (The reference has no counterpart: Matlab allocates per call,
+ * polyphase_synthesis.m:152-156.) */
+int pfb_inverse_reserve(pfb_inverse_plan* plan, int npol, long long n_dat, int ngroups);
 /* run only one stage of the chain over the whole input (profiling / roofline):
  * stage 0 = channel IDFT into the caller's v buffer [n_dat][nchan][npol],
  * stage 1 = overlap-save resampling from such a v buffer. */
@@ -138,6 +144,15 @@ int pfb_purity_metrics(const void* args_dev, int nvec, int dtype, void* stream);
 
 /* kernels launched by this library since load (bench.py "gpu_launches") */
 long long pfb_launch_count(void);
+
+/* ---- integer DADA payloads: replaces the int8 / int16 -> floating-point cast of matlab/DADARead.m:41-53,66-70
+ *      (and psr_formats.DADAFile.load_data on NBIT 8/16 files) and the integer write of
+ *      matlab/write_dada_header.m:15-22 + FilterBank.m:106-113 (round(scale*x), ties away from zero, saturating
+ *      like Matlab's int16()).  nvalues counts REAL values (2 per complex sample); buffers are 16-byte aligned
+ *      device pointers.  The conversion is exact, so results equal a host-side cast bit for bit. */
+int pfb_unpack_payload(const void* in_dev, void* out_dev, long long nvalues, int nbit, int dtype, void* stream);
+int pfb_pack_payload(const void* in_dev, void* out_dev, long long nvalues, int nbit, int dtype, double scale,
+                     void* stream);
 
 #ifdef __cplusplus
 }

@@ -562,6 +562,17 @@ _ANALYSIS = {
 }
 
 
+def matlab_round(z):
+    """Matlab `round` (FilterBank.m:82,112): ties go AWAY from zero, applied to the real and
+    imaginary parts separately (numpy's `round` sends ties to the even integer)."""
+    z = np.asarray(z)
+    def r(a):
+        return np.sign(a) * np.floor(np.abs(a) + 0.5)
+    if np.iscomplexobj(z):
+        return (r(z.real) + 1j * r(z.imag)).astype(z.dtype)
+    return r(z).astype(z.dtype)
+
+
 class FilterBank:
     """matlab/FilterBank.m:65-128 (tail buffering, trim to multiple of nu,
     optional integer rounding)."""
@@ -590,7 +601,7 @@ class FilterBank:
             scale = 1.0
             if self.rms_input > 0:
                 scale = self.rms_input / np.sqrt(np.var(x, ddof=1))
-            x = np.round(scale * x)
+            x = matlab_round(scale * x)
         if self.buffered_samples > 0:                               # :85-88
             x = np.concatenate([self.input_buffer, x], axis=2)
             self.buffered_samples = 0
@@ -603,7 +614,7 @@ class FilterBank:
             scale = 1.0
             if self.rms_output:
                 scale = self.rms_output / np.sqrt(np.var(out, ddof=1))
-            out = np.round(scale * out)
+            out = matlab_round(scale * out)
         input_idat = out.shape[2] * self.n_chan * self.os_factor.de // self.os_factor.nu   # :119
         self.buffered_samples = n_in - input_idat
         if self.buffered_samples > 0:

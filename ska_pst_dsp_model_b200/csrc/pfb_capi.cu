@@ -14,6 +14,7 @@
 #include "pfb_generic.cuh"
 #include "pfb_low.cuh"
 #include "pfb_mid.cuh"
+#include "pfb_payload.cuh"
 #include "pfb_purity.cuh"
 
 using namespace pfb;
@@ -149,6 +150,7 @@ struct pfb_analysis_plan {
   const void* d_taps = nullptr;     // T[fl]
   const void* d_low_taps = nullptr; // fast Low kernel tap layout
   bool low_fast = false;
+  bool mid_fast = true;             // shape-specialised SKA-Mid kernels allowed (PFB_NO_MID, read once at plan creation)
   void* d_yscratch = nullptr;       // arm sums of the sliding-window FIR kernel
   size_t yscratch_cap = 0;
   DeviceTables tabs;
@@ -169,6 +171,8 @@ struct pfb_inverse_plan {
   std::vector<double> deripple_w;    // FN-order deripple weights (kept for set_spectral_taper)
   const void* d_low = nullptr;       // fast-path tables (pfb_low.cuh)
   bool low_fast = false;
+  bool mid_fast = true;              // PFB_NO_MID / PFB_NO_WS: debugging switches, read once at plan creation
+  bool ws_fast = true;
   long long scratch_bytes = 1024ll << 20;   // one chunk for streams up to ~2^25 samples/pol at the SKA-Low shape
   void* d_scratch = nullptr;
   size_t scratch_cap = 0;
@@ -233,6 +237,7 @@ int pfb_analysis_plan_create(pfb_analysis_plan** plan, int variant, int nchan, i
   pfb_analysis_plan* p = new pfb_analysis_plan();
   p->variant = variant; p->N = nchan; p->nu = os_nu; p->de = os_de; p->dtype = dtype; p->device = device;
   p->ntaps = ntaps;
+  p->mid_fast = getenv("PFB_NO_MID") == nullptr;
   p->S = (int)(((long long)nchan * os_de) / os_nu);          // polyphase_analysis.m:56
   p->P = (ntaps + nchan - 1) / nchan;                         // pad_filter.m:10
   p->fl = p->P * nchan;
@@ -379,7 +384,7 @@ static int slide_go(pfb_analysis_plan* p, const AnalysisArgs& a, cudaStream_t st
   // for every step whose rows lie in the whole-row part of the stream; the last few steps keep the checked loads
   long long i_fast = 0;
   if (fir_phases_applies<T, P, DE>(p->nu) && a.npol == 2 && a.N % mid::kPhArms == 0 && a.start0 % a.N == 0 &&
-      ((uintptr_t)a.in % 16 == 0) && !getenv("PFB_NO_MID")) {
+      ((uintptr_t)a.in % 16 == 0) && p->mid_fast) {
     const long long rows_full = a.n_dat / a.N;
     const long long row0 = a.start0 / a.N;                       // exact (may be negative)
     // step i reads rows row0 + Q, Q <= (nu - 1) + DE * i + P - 1
@@ -396,8 +401,7 @@ static int slide_go(pfb_analysis_plan* p, const AnalysisArgs& a, cudaStream_t st
   }
   int rc = launch_slide(i_fast, nsteps);
   if (rc) return rc;
-  if (std::is_same<T, float>::value && a.N == 4096 && a.npol == 2 && ((uintptr_t)a.out % 16 == 0) &&
-      !getenv("PFB_NO_MID")) {
+  if (std::is_same<T, float>::value && a.N == 4096 && a.npol == 2 && ((uintptr_t)a.out % 16 == 0) && p->mid_fast) {
     // 4096-channel fast path: one register-resident 16x16x16 transform per (block, both pols)
     mid::RowFftArgs m;
     m.in = p->d_yscratch; m.out = a.out; m.tw = reinterpret_cast<const float2*>(a.fft.tw); m.jmap = nullptr;
@@ -609,6 +613,8 @@ int pfb_inverse_plan_create(pfb_inverse_plan** plan, int nchan, int os_nu, int o
   pfb_inverse_plan* p = new pfb_inverse_plan();
   p->nchan = nchan; p->nu = os_nu; p->de = os_de; p->Nf = nfft; p->ov = overlap; p->dtype = dtype; p->device = device;
   p->keep = nfft - 2 * overlap;
+  p->mid_fast = getenv("PFB_NO_MID") == nullptr;
+  p->ws_fast = getenv("PFB_NO_WS") == nullptr;
   p->FNw = (int)(((long long)nfft * os_de) / os_nu);          // polyphase_synthesis.m:133
   p->ov2 = (int)(((long long)overlap * os_de) / os_nu);
   p->keep2 = p->FNw - 2 * p->ov2;
@@ -658,7 +664,7 @@ static int launch_chan_idft(pfb_inverse_plan* p, const void* in, void* out, int 
     if (done) { p->prof_end(tok, st); return check_launch("pfb_chan_idft_low"); }
   }
   if (std::is_same<T, float>::value && p->nchan == 4096 && npol == 2 && ((uintptr_t)in % 16 == 0) &&
-      ((uintptr_t)out % 16 == 0) && !getenv("PFB_NO_MID")) {
+      ((uintptr_t)out % 16 == 0) && p->mid_fast) {
     mid::RowFftArgs m;
     memset(&m, 0, sizeof(m));
     m.in = in; m.out = out; m.tw = reinterpret_cast<const float2*>(p->fft_chan.tw); m.jmap = p->d_jmap; m.nrows = nrows;
@@ -729,7 +735,7 @@ static int launch_resample(pfb_inverse_plan* p, const void* v, void* out, int np
 
 template <typename T>
 static int inverse_run(pfb_inverse_plan* p, const void* in, void* out, int npol, long long n_dat, cudaStream_t st,
-                       int G = 1) {
+                       int G = 1, bool dry_run = false) {
   const long long nblocks = pfb_inverse_nblocks(p, n_dat);
   if (nblocks <= 0) return PFB_OK;
   const long long rowbytes = (long long)p->nchan * G * npol * sizeof(Cx<T>);
@@ -742,11 +748,18 @@ static int inverse_run(pfb_inverse_plan* p, const void* in, void* out, int npol,
   if (B > nblocks) B = nblocks;
   const size_t need = (size_t)(((B - 1) * p->keep + p->Nf) * rowbytes);
   if (need > p->scratch_cap) {
+    // (a CUDA graph captured before this call would hold the old scratch pointer: size the plan with
+    //  pfb_inverse_reserve before capturing)
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(st, &cs);
+    if (cs != cudaStreamCaptureStatusNone)
+      return fail(PFB_ERR_ARG, "inversion scratch must grow (%zu > %zu bytes) during stream capture: call pfb_inverse_reserve first", need, p->scratch_cap);
     if (p->d_scratch) CU(cudaFree(p->d_scratch));
     p->d_scratch = nullptr; p->scratch_cap = 0;
     CU(cudaMalloc(&p->d_scratch, need));
     p->scratch_cap = need;
   }
+  if (dry_run) return PFB_OK;
   const long long rowlen = (long long)p->nchan * G * npol;
   for (long long n0 = 0; n0 < nblocks; n0 += B) {
     const long long nb = (nblocks - n0 < B) ? nblocks - n0 : B;
@@ -754,7 +767,7 @@ static int inverse_run(pfb_inverse_plan* p, const void* in, void* out, int npol,
     const Cx<T>* src = reinterpret_cast<const Cx<T>*>(in) + n0 * p->keep * rowlen;
     Cx<T>* dst = reinterpret_cast<Cx<T>*>(out) + n0 * p->keep2 * rowlen;
     // SKA-Low dual-pol shape: grouped scratch layout + warp-autonomous resample kernel
-    const bool ws = p->low_fast && std::is_same<T, float>::value && low_ws_ok(p->d_low, npol, G, src, dst);
+    const bool ws = p->low_fast && p->ws_fast && std::is_same<T, float>::value && low_ws_ok(p->d_low, npol, G, src, dst);
     int rc = launch_chan_idft<T>(p, src, p->d_scratch, npol, rows * G, st, ws);  // every (tau, group) is one row
     if (rc) return rc;
     rc = launch_resample<T>(p, p->d_scratch, dst, npol, nb, st, G, ws, rows);
@@ -866,6 +879,15 @@ static int inverse_run_literal(pfb_inverse_plan* p, const void* in, void* out, i
     }
   }
   return PFB_OK;
+}
+
+int pfb_inverse_reserve(pfb_inverse_plan* p, int npol, long long n_dat, int ngroups) {
+  if (!p) return fail(PFB_ERR_ARG, "null plan");
+  if (npol < 1 || npol > 2 || ngroups < 1) return fail(PFB_ERR_ARG, "pfb_inverse_reserve: bad argument");
+  if (p->spectral) return PFB_OK;     // the literal chain sizes its scratch per call (not graph-capturable while growing)
+  CU(cudaSetDevice(p->device));
+  return p->dtype == PFB_DTYPE_C64 ? inverse_run<float>(p, nullptr, nullptr, npol, n_dat, nullptr, ngroups, true)
+                                   : inverse_run<double>(p, nullptr, nullptr, npol, n_dat, nullptr, ngroups, true);
 }
 
 int pfb_inverse_set_profiling(pfb_inverse_plan* p, int on) {
@@ -992,4 +1014,38 @@ int pfb_purity_metrics(const void* args_dev, int nvec, int dtype, void* stream) 
   else if (dtype == PFB_DTYPE_C128) pfb_metrics_kernel<double><<<nvec, 1024, 0, st>>>(a);
   else return fail(PFB_ERR_ARG, "dtype must be 0 (c64) or 1 (c128)");
   return check_launch("pfb_metrics_kernel");
+}
+
+// ---------------------------------------------------------------------------
+// integer DADA payloads (NBIT 8 / 16) <-> the arithmetic type, on the device
+int pfb_unpack_payload(const void* in_dev, void* out_dev, long long nvalues, int nbit, int dtype, void* stream) {
+  if (nvalues < 0 || (nbit != 8 && nbit != 16)) return fail(PFB_ERR_ARG, "pfb_unpack_payload: nbit must be 8 or 16");
+  if (dtype != PFB_DTYPE_C64 && dtype != PFB_DTYPE_C128) return fail(PFB_ERR_ARG, "dtype must be 0 (c64) or 1 (c128)");
+  if (nvalues == 0) return PFB_OK;
+  if (!in_dev || !out_dev) return fail(PFB_ERR_ARG, "null pointer");
+  if ((uintptr_t)in_dev % 16 || (uintptr_t)out_dev % 16) return fail(PFB_ERR_ARG, "pfb_unpack_payload: buffers must be 16-byte aligned");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  long long grid = (nvalues / 8 + 255) / 256;
+  if (grid > 148 * 16) grid = 148 * 16;
+  if (grid < 1) grid = 1;
+  if (nbit == 8 && dtype == PFB_DTYPE_C64) pfb_unpack_kernel<signed char, float><<<(unsigned)grid, 256, 0, st>>>((const signed char*)in_dev, (float*)out_dev, nvalues);
+  else if (nbit == 8) pfb_unpack_kernel<signed char, double><<<(unsigned)grid, 256, 0, st>>>((const signed char*)in_dev, (double*)out_dev, nvalues);
+  else if (dtype == PFB_DTYPE_C64) pfb_unpack_kernel<short, float><<<(unsigned)grid, 256, 0, st>>>((const short*)in_dev, (float*)out_dev, nvalues);
+  else pfb_unpack_kernel<short, double><<<(unsigned)grid, 256, 0, st>>>((const short*)in_dev, (double*)out_dev, nvalues);
+  return check_launch("pfb_unpack_kernel");
+}
+
+int pfb_pack_payload(const void* in_dev, void* out_dev, long long nvalues, int nbit, int dtype, double scale, void* stream) {
+  if (nvalues < 0 || (nbit != 8 && nbit != 16)) return fail(PFB_ERR_ARG, "pfb_pack_payload: nbit must be 8 or 16");
+  if (dtype != PFB_DTYPE_C64 && dtype != PFB_DTYPE_C128) return fail(PFB_ERR_ARG, "dtype must be 0 (c64) or 1 (c128)");
+  if (nvalues == 0) return PFB_OK;
+  if (!in_dev || !out_dev) return fail(PFB_ERR_ARG, "null pointer");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  long long grid = (nvalues + 255) / 256;
+  if (grid > 148 * 16) grid = 148 * 16;
+  if (nbit == 8 && dtype == PFB_DTYPE_C64) pfb_pack_kernel<float, signed char><<<(unsigned)grid, 256, 0, st>>>((const float*)in_dev, (signed char*)out_dev, nvalues, (float)scale);
+  else if (nbit == 8) pfb_pack_kernel<double, signed char><<<(unsigned)grid, 256, 0, st>>>((const double*)in_dev, (signed char*)out_dev, nvalues, scale);
+  else if (dtype == PFB_DTYPE_C64) pfb_pack_kernel<float, short><<<(unsigned)grid, 256, 0, st>>>((const float*)in_dev, (short*)out_dev, nvalues, (float)scale);
+  else pfb_pack_kernel<double, short><<<(unsigned)grid, 256, 0, st>>>((const double*)in_dev, (short*)out_dev, nvalues, scale);
+  return check_launch("pfb_pack_kernel");
 }

@@ -38,9 +38,6 @@ namespace pfb {
 namespace low {
 
 typedef Cx<float> C;
-#ifndef K1VAR
-#define K1VAR 0
-#endif
 
 // a * exp(DIR * 2 pi i k / N), k known after unrolling
 template <int N, int DIR> __device__ __forceinline__ C mul_lit(C a, int k) {
@@ -246,7 +243,6 @@ __global__ void __launch_bounds__(64 * NPOL, NPOL == 2 ? 2 : 4) pfb_analysis_low
       for (int o = 0; o < 4; ++o) ex[(size_t)((j * NPOL + pol) * 4 + o) * kExStride + r] = z[o];
     }
     __syncthreads();
-#if K1VAR != 1
     {
       // one 64-point FFT per thread (task = block j, pol, o), two radix-8 passes over the
       // thread's private row in shared memory (the 48-sample window keeps the registers)
@@ -284,7 +280,6 @@ __global__ void __launch_bounds__(64 * NPOL, NPOL == 2 ? 2 : 4) pfb_analysis_low
         if (o1 & 1) asm volatile("" ::: "memory");
       }
     }
-#endif
     __syncthreads();
   }
 }
@@ -360,66 +355,8 @@ __global__ void __launch_bounds__(256, 3) pfb_chan_idft_low(const ChanArgs a) {
   }
 }
 
-// Dual-pol variant: one lane carries both polarisations of its 16 channels, so every global and
-// shared access is 128 bits wide (both pols of a channel are adjacent in TFP order) and the
-// inter-pass twiddles are shared by the two transforms.
-__global__ void __launch_bounds__(128, 4) pfb_chan_idft_low_p2(const ChanArgs a) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  float4* ex = reinterpret_cast<float4*>(smem_raw);    // [2][8 rows][273] (pol0.re, pol0.im, pol1.re, pol1.im)
-  const int tid = threadIdx.x;
-  const int q = tid & 15, rsub = tid >> 4;
-  constexpr int ROWS = 8;
-  C tw[15];
-#pragma unroll
-  for (int o = 1; o < 16; ++o) {
-    float2 v = __ldg(a.tw256 + ((q * o) & 255));
-    tw[o - 1] = mk<float>(v.x, -v.y);
-  }
-  const long long npass = (a.nrows + ROWS - 1) / ROWS;
-  int buf = 0;
-  for (long long ps = blockIdx.x; ps < npass; ps += gridDim.x, buf ^= 1) {
-    const long long row = ps * ROWS + rsub;
-    float4* e = ex + (size_t)buf * ROWS * kColStride + (size_t)rsub * kColStride;
-    C x0[16], x1[16];
-    if (row < a.nrows) {
-      const float4* p = reinterpret_cast<const float4*>(a.in) + row * 256 + q;
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const float4 v = __ldg(p + i * 16);
-        x0[i] = mk<float>(v.x, v.y);
-        x1[i] = mk<float>(v.z, v.w);
-      }
-      fft_reg<4, 4, +1>(x0);
-      fft_reg<4, 4, +1>(x1);
-#pragma unroll
-      for (int o = 0; o < 16; ++o) {
-        C u0 = x0[slot<4, 4>(o)], u1 = x1[slot<4, 4>(o)];
-        if (o) { u0 = u0 * tw[o - 1]; u1 = u1 * tw[o - 1]; }
-        e[o * kQStride + q] = make_float4(u0.x, u0.y, u1.x, u1.y);
-      }
-    }
-    __syncthreads();
-    if (row < a.nrows) {
-      const int o = q;
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const float4 v = e[o * kQStride + i];
-        x0[i] = mk<float>(v.x, v.y);
-        x1[i] = mk<float>(v.z, v.w);
-      }
-      fft_reg<4, 4, +1>(x0);
-      fft_reg<4, 4, +1>(x1);
-      float4* p = reinterpret_cast<float4*>(a.out) + row * 256 + o;
-#pragma unroll
-      for (int o2 = 0; o2 < 16; ++o2) {
-        const C u0 = x0[slot<4, 4>(o2)], u1 = x1[slot<4, 4>(o2)];
-        p[o2 * 16] = make_float4(u0.x, u0.y, u1.x, u1.y);
-      }
-    }
-  }
-}
-
-// TMA-fed variant of the dual-pol kernel: whole rows (4 KiB, contiguous in TFP order) are
+// TMA-fed dual-pol kernel (one lane carries both polarisations of its 16 channels, every access 128 bits
+// wide): whole rows (4 KiB, contiguous in TFP order) are
 // streamed by cp.async.bulk into a 3-stage ring, so no warp ever waits on a global load, and
 // because the 16 lanes of a transform live in one warp the two passes exchange data through the
 // ring slot itself with __syncwarp() only - the CTA never executes a block-wide barrier.
@@ -1064,8 +1001,7 @@ int low_chan_idft_launch(const void* d_low, const void* in, void* out, int npol,
 // true when the warp-autonomous resample kernel (and the grouped scratch layout it reads) applies
 inline bool low_ws_ok(const void* d_low, int npol, int groups_b, const void* in, const void* out) {
   const low::LowInverse* h = reinterpret_cast<const low::LowInverse*>(d_low);
-  static const bool off = getenv("PFB_NO_WS") != nullptr;
-  return !off && h->chan_fast && npol == 2 && groups_b == 1 && h->ov2 == 36 && h->keep == 160 && !h->flip &&
+  return h->chan_fast && npol == 2 && groups_b == 1 && h->ov2 == 36 && h->keep == 160 && !h->flip &&
          ((uintptr_t)in % 16 == 0) && ((uintptr_t)out % 16 == 0);
 }
 

@@ -10,7 +10,7 @@ import numpy as np
 from .. import partialize as _partialize
 from ..formats import DADAFile
 from . import util
-from .config import build_dir, config
+from .config import build_dir, config, config_dir
 
 __all__ = ["complex_sinusoid", "time_domain_impulse", "generate_test_vector"]
 
@@ -55,6 +55,8 @@ def generate_test_vector(*args, n_bins: int, domain_name: str, header_template: 
     ``generator([offset], [width], domain_name="time")`` -> DADAFile of shape (n_bins, 1, n_pol)."""
     if output_dir is None:
         output_dir = "./"
+    if header_template is None:                       # generate_test_vector.py:121-123 of the reference
+        header_template = os.path.join(config_dir, config["header_file_path"])
     if len(args) > 0:
         args_list = []
         for arg in args:

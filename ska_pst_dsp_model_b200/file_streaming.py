@@ -9,6 +9,9 @@ on three CUDA streams, and written at its final offset of the output file by a w
 ``depth`` pieces in flight.  Pieces carry their own FIR history / overlap-save overlap (re-read from the
 file), so the result is bit-identical to the whole-file operators of ``format_handler``.
 
+Integer payloads (NBIT 8 / 16, DADARead.m:41-53) travel as integers - disk, pinned memory and PCIe carry 2-4x fewer
+bytes - and are cast to the arithmetic type on the device (``pfb_unpack_payload``), bit-identically to a host cast.
+
 The padded (SKA-Mid) analysis wraps its output circularly (polyphase_analysis_padded.m:156) and is not
 streamable; ``stream_channelize`` refuses it.
 """
@@ -24,36 +27,68 @@ from .rational import Rational
 
 
 def _payload_info(path):
+    """(header, arithmetic complex dtype, payload offset, samples, NBIT).  NBIT 32 / 64 payloads are complex floats;
+    NBIT 8 / 16 are (re, im) integer pairs (DADARead.m:41-53) that travel as integers and are cast on the device."""
     hdr = read_header(path)
-    if int(hdr.get("NDIM", "2")) != 2 or int(hdr["NBIT"]) not in (32, 64):
-        raise ValueError("streaming operators need a complex float32 / float64 payload (NDIM 2, NBIT 32 or 64)")
-    cdt = np.complex64 if int(hdr["NBIT"]) == 32 else np.complex128
+    nbit = int(hdr["NBIT"])
+    if int(hdr.get("NDIM", "2")) != 2 or nbit not in (8, 16, 32, 64):
+        raise ValueError("streaming operators need a complex payload (NDIM 2) with NBIT 8, 16, 32 or 64")
+    cdt = np.complex128 if nbit == 64 else np.complex64
     off = int(hdr["HDR_SIZE"])
     per = int(hdr["NCHAN"]) * int(hdr["NPOL"])
-    ndat = (os.path.getsize(path) - off) // (per * np.dtype(cdt).itemsize)
-    return hdr, cdt, off, ndat
+    ndat = (os.path.getsize(path) - off) // (per * 2 * nbit // 8)
+    return hdr, cdt, off, ndat, nbit
+
+
+def _int_input(torch, nbit):
+    """(torch dtype of the travelling payload, elements per complex sample) for an NBIT 8 / 16 payload, else None."""
+    return {8: (torch.int8, 2), 16: (torch.int16, 2)}.get(nbit)
+
+
+def _unpacker(torch, device, nbit, max_complex, tdtype):
+    """Device-side int -> complex cast (pfb_unpack_payload) into one staging buffer owned by the pipeline."""
+    import ctypes
+    from . import lib as _l
+    stage = torch.empty((max_complex,), dtype=tdtype, device=device)
+    code = _l.PFB_DTYPE_C64 if tdtype == torch.complex64 else _l.PFB_DTYPE_C128
+
+    def unpack(din_int, ncomplex):
+        st = ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+        _l.check(_l.lib.pfb_unpack_payload(din_int.data_ptr(), stage.data_ptr(), 2 * ncomplex, nbit, code, st))
+        return stage[:ncomplex]
+    return unpack
 
 
 class _Pipe:
-    """depth-deep ring of (pinned in, device in, device out, pinned out) buffers + the three streams."""
+    """depth-deep ring of (pinned in, device in, device out, pinned out) buffers + the three streams.
 
-    def __init__(self, torch, device, depth, in_shape, out_shape, tdtype):
+    Every buffer is guarded by the event (or future) of ITS last user only, so `depth` pieces are genuinely in
+    flight: disk read of piece i+depth-1, H2D of piece i+1, kernels of piece i, D2H of piece i-1 and the disk write
+    of piece i-2 overlap."""
+
+    def __init__(self, torch, device, depth, in_shape, out_shape, tdtype, in_dtype=None):
         self.torch, self.depth = torch, depth
-        self.hin = [torch.empty(in_shape, dtype=tdtype).pin_memory() for _ in range(depth)]
+        in_dtype = in_dtype or tdtype
+        self.hin = [torch.empty(in_shape, dtype=in_dtype).pin_memory() for _ in range(depth)]
         self.hout = [torch.empty(out_shape, dtype=tdtype).pin_memory() for _ in range(depth)]
-        self.din = [torch.empty(in_shape, dtype=tdtype, device=device) for _ in range(depth)]
+        self.din = [torch.empty(in_shape, dtype=in_dtype, device=device) for _ in range(depth)]
         self.dout = [torch.empty(out_shape, dtype=tdtype, device=device) for _ in range(depth)]
         self.s_in, self.s_cmp, self.s_out = (torch.cuda.Stream(device) for _ in range(3))
-        self.ev_free = [None] * depth        # compute finished with din[slot]
-        self.ev_done = [None] * depth        # D2H into hout[slot] finished
+        self.ev_h2d = [None] * depth         # H2D out of hin[slot] finished  -> the reader may refill hin[slot]
+        self.ev_free = [None] * depth        # kernels finished with din[slot] -> the next H2D may overwrite it
+        self.ev_done = [None] * depth        # D2H out of dout[slot] finished  -> the next kernels may overwrite it
         self.wr = [None] * depth             # writer future still reading hout[slot]
-        self.io = ThreadPoolExecutor(max_workers=2)
+        self.reader = ThreadPoolExecutor(max_workers=1)
+        self.writer = ThreadPoolExecutor(max_workers=1)
 
     def close(self):
-        self.io.shutdown(wait=True)
+        self.reader.shutdown(wait=True)
+        self.writer.shutdown(wait=True)
 
 
-def _read_into(path, offset, dst_numpy):
+def _read_into(path, offset, dst_numpy, event):
+    if event is not None:
+        event.synchronize()                  # the H2D copy that last read this pinned buffer
     with open(path, "rb", buffering=0) as f:
         f.seek(offset)
         view = memoryview(dst_numpy).cast("B")
@@ -67,7 +102,10 @@ def _read_into(path, offset, dst_numpy):
 
 def _write_from(fd, offset, src_numpy, event):
     event.synchronize()
-    os.pwrite(fd, memoryview(src_numpy).cast("B"), offset)
+    view = memoryview(src_numpy).cast("B")
+    done = 0
+    while done < len(view):                  # pwrite may write less than asked
+        done += os.pwrite(fd, view[done:], offset + done)
 
 
 def _run(pipe, pieces, in_path, in_item, fd_out, out_item, compute):
@@ -78,41 +116,38 @@ def _run(pipe, pieces, in_path, in_item, fd_out, out_item, compute):
 
     def start_read(i):
         slot = i % pipe.depth
-        if pipe.wr[slot] is not None:        # the writer of the piece that used this slot's buffers has long finished
-            pipe.wr[slot].result()
         ib, ie = pieces[i][0], pieces[i][1]
         dst = pipe.hin[slot].view(-1)[:ie].numpy()
-        reads[i] = pipe.io.submit(_read_into, in_path, ib, dst)
+        reads[i] = pipe.reader.submit(_read_into, in_path, ib, dst, pipe.ev_h2d[slot])
 
-    for i in range(min(pipe.depth - 1, len(pieces))):
+    for i in range(min(pipe.depth, len(pieces))):
         start_read(i)
     for i, (ib, ie, ob, oe, args) in enumerate(pieces):
         slot = i % pipe.depth
-        nxt = i + pipe.depth - 1
-        if nxt < len(pieces):
-            if pipe.ev_done[nxt % pipe.depth] is not None:
-                pipe.ev_done[nxt % pipe.depth].synchronize()
-            start_read(nxt)
-        reads.pop(i).result()
+        reads.pop(i).result()                               # piece i is in pinned memory
         with torch.cuda.stream(pipe.s_in):
             if pipe.ev_free[slot] is not None:
                 pipe.s_in.wait_event(pipe.ev_free[slot])
             pipe.din[slot].view(-1)[:ie].copy_(pipe.hin[slot].view(-1)[:ie], non_blocking=True)
-            ev_in = torch.cuda.Event()
-            ev_in.record(pipe.s_in)
+            pipe.ev_h2d[slot] = torch.cuda.Event()
+            pipe.ev_h2d[slot].record(pipe.s_in)
+        if i + pipe.depth < len(pieces):
+            start_read(i + pipe.depth)                      # refills hin[slot] once the copy above has drained it
         with torch.cuda.stream(pipe.s_cmp):
-            pipe.s_cmp.wait_event(ev_in)
+            pipe.s_cmp.wait_event(pipe.ev_h2d[slot])
             if pipe.ev_done[slot] is not None:
                 pipe.s_cmp.wait_event(pipe.ev_done[slot])
             compute(pipe.din[slot].view(-1)[:ie], pipe.dout[slot].view(-1)[:oe], args)
             pipe.ev_free[slot] = torch.cuda.Event()
             pipe.ev_free[slot].record(pipe.s_cmp)
+        if pipe.wr[slot] is not None:
+            pipe.wr[slot].result()                          # hout[slot]: the write of piece i - depth (long finished)
         with torch.cuda.stream(pipe.s_out):
             pipe.s_out.wait_event(pipe.ev_free[slot])
             pipe.hout[slot].view(-1)[:oe].copy_(pipe.dout[slot].view(-1)[:oe], non_blocking=True)
             pipe.ev_done[slot] = torch.cuda.Event()
             pipe.ev_done[slot].record(pipe.s_out)
-        pipe.wr[slot] = pipe.io.submit(_write_from, fd_out, ob, pipe.hout[slot].view(-1)[:oe].numpy(), pipe.ev_done[slot])
+        pipe.wr[slot] = pipe.writer.submit(_write_from, fd_out, ob, pipe.hout[slot].view(-1)[:oe].numpy(), pipe.ev_done[slot])
     for w in pipe.wr:
         if w is not None:
             w.result()
@@ -124,7 +159,8 @@ def stream_channelize(channelizer, input_file_path, output_dir="./", output_file
     payload on disk; ``load_data()`` reads it)."""
     from .format_handler import _fmt_num, _tdtype, _torch
     torch = _torch()
-    hdr, cdt, off, ndat = _payload_info(input_file_path)
+    hdr, cdt, off, ndat, nbit = _payload_info(input_file_path)
+    intin = _int_input(torch, nbit)
     if int(hdr["NCHAN"]) != 1:
         raise ValueError("expected single-channel input")
     npol = int(hdr["NPOL"])
@@ -138,7 +174,8 @@ def stream_channelize(channelizer, input_file_path, output_dir="./", output_file
     nblocks = plan.nblocks(ndat, first_call)
     S, fl, nco = plan.step, plan.fl, plan.nchan_out
     pre = 1536 if plan.variant == 2 else 0                  # lowcbf pre-pad (PSTFilterbank.m:27-34)
-    item = np.dtype(cdt).itemsize
+    item = np.dtype(cdt).itemsize                                 # output (and arithmetic) sample size
+    in_item, in_per = (2 * nbit // 8, intin[1]) if intin else (item, 1)   # bytes / travelling elements per input sample
     if output_file_name is None:
         output_file_name = "channelized." + os.path.basename(input_file_path)
     of = DADAFile(os.path.join(output_dir, output_file_name), header=hdr)
@@ -158,7 +195,7 @@ def stream_channelize(channelizer, input_file_path, output_dir="./", output_file
         k1 = min(nblocks, k0 + blocks_per_piece)
         s0 = max(0, k0 * S - pre)
         s1 = min(ndat, (k1 - 1) * S - pre + fl)
-        pieces.append((off + s0 * npol * item, (s1 - s0) * npol, len(head) + k0 * nco * npol * item,
+        pieces.append((off + s0 * npol * in_item, (s1 - s0) * npol * in_per, len(head) + k0 * nco * npol * item,
                        (k1 - k0) * nco * npol, (s0, k0, k1 - k0, s1 - s0)))
     max_in = max((p[1] for p in pieces), default=0)
     max_out = max((p[3] for p in pieces), default=0)
@@ -166,19 +203,23 @@ def stream_channelize(channelizer, input_file_path, output_dir="./", output_file
     try:
         os.pwrite(fd, head, 0)
         if pieces:
-            pipe = _Pipe(torch, plan.device, depth, (max_in,), (max_out,), _tdtype(cdt))
+            pipe = _Pipe(torch, plan.device, depth, (max_in,), (max_out,), _tdtype(cdt), intin[0] if intin else None)
+            unpack = _unpacker(torch, plan.device, nbit, max_in // in_per, _tdtype(cdt)) if intin else None
 
             def compute(din, dout, args):
                 s0, k0, nb, ns = args
+                if unpack is not None:
+                    din = unpack(din, ns * npol)
                 plan.segment(din.view(ns, npol), s0, k0, nb, out=dout.view(nb, nco, npol), first_call=first_call)
 
             try:
-                _run(pipe, pieces, input_file_path, item, fd, item, compute)
+                _run(pipe, pieces, input_file_path, in_item, fd, item, compute)
             finally:
                 pipe.close()
     finally:
         os.close(fd)
     of.header = read_header(of.file_path)
+    of._lazy = True                       # .data maps the payload on first access (no copy into memory here)
     return of
 
 
@@ -187,7 +228,8 @@ def stream_synthesize(synthesizer, input_file_path, output_dir="./", output_file
     """``format_handler.PSRFormatSynthesizer`` on a file of any length."""
     from .format_handler import _fmt_num, _tdtype, _torch
     torch = _torch()
-    hdr, cdt, off, ndat = _payload_info(input_file_path)
+    hdr, cdt, off, ndat, nbit = _payload_info(input_file_path)
+    intin = _int_input(torch, nbit)
     nchan, npol = int(hdr["NCHAN"]), int(hdr["NPOL"])
     os_factor = Rational.from_str(hdr["OS_FACTOR"])
     taps = None
@@ -200,6 +242,7 @@ def stream_synthesize(synthesizer, input_file_path, output_dir="./", output_file
     keep, nf = synthesizer.input_fft_length - 2 * synthesizer.input_overlap, synthesizer.input_fft_length
     okeep = plan.out_len(keep + 2 * synthesizer.input_overlap)        # output samples per block
     item = np.dtype(cdt).itemsize
+    in_item, in_per = (2 * nbit // 8, intin[1]) if intin else (item, 1)
     if output_file_name is None:
         output_file_name = "synthesized." + os.path.basename(input_file_path)
     of = DADAFile(os.path.join(output_dir, output_file_name), header=hdr)
@@ -212,7 +255,7 @@ def stream_synthesize(synthesizer, input_file_path, output_dir="./", output_file
     for n0 in range(0, nblocks, blocks_per_piece):
         n1 = min(nblocks, n0 + blocks_per_piece)
         rows = (n1 - n0 - 1) * keep + nf
-        pieces.append((off + n0 * keep * row * item, rows * row, len(head) + n0 * okeep * npol * item,
+        pieces.append((off + n0 * keep * row * in_item, rows * row * in_per, len(head) + n0 * okeep * npol * item,
                        (n1 - n0) * okeep * npol, (rows, n1 - n0)))
     max_in = max((p[1] for p in pieces), default=0)
     max_out = max((p[3] for p in pieces), default=0)
@@ -220,17 +263,21 @@ def stream_synthesize(synthesizer, input_file_path, output_dir="./", output_file
     try:
         os.pwrite(fd, head, 0)
         if pieces:
-            pipe = _Pipe(torch, plan.device, depth, (max_in,), (max_out,), _tdtype(cdt))
+            pipe = _Pipe(torch, plan.device, depth, (max_in,), (max_out,), _tdtype(cdt), intin[0] if intin else None)
+            unpack = _unpacker(torch, plan.device, nbit, max_in // in_per, _tdtype(cdt)) if intin else None
 
             def compute(din, dout, args):
                 rows, nb = args
+                if unpack is not None:
+                    din = unpack(din, rows * row)
                 plan(din.view(rows, nchan, npol), out=dout.view(nb * okeep, npol))
 
             try:
-                _run(pipe, pieces, input_file_path, item, fd, item, compute)
+                _run(pipe, pieces, input_file_path, in_item, fd, item, compute)
             finally:
                 pipe.close()
     finally:
         os.close(fd)
     of.header = read_header(of.file_path)
+    of._lazy = True                       # .data maps the payload on first access (no copy into memory here)
     return of

@@ -88,6 +88,10 @@ def resolve_fir_filter(path, config=None, config_dir=None):
     nu, de = (int(v) for v in str(config["os_factor"]).split("/"))
     key = (design, config["channels"], nu, de, config["fir_filter_taps"])
     if key not in _DESIGN_CACHE:
+        import logging
+        logging.getLogger(__name__).warning(
+            "FIR coefficient file %s not found: re-creating the %s design with scipy.signal.firls "
+            "(coefficients will differ in the last digits from the Matlab firls design)", path, design)
         cache = os.path.join(_DATA, "designed", f"{design}.{nu}-{de}.{config['channels']}.{config['fir_filter_taps']}.npy")
         if os.path.exists(cache):
             _DESIGN_CACHE[key] = np.load(cache)

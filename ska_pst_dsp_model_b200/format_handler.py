@@ -78,13 +78,13 @@ class PSRFormatChannelizer:
         return out.cpu().numpy()
 
     def __call__(self, input_data_file, output_dir="./", output_file_name=None):
-        if input_data_file.data is None and _stream_it(input_data_file.file_path) and \
+        if input_data_file._data is None and _stream_it(input_data_file.file_path) and \
                 self.analysis_function != "polyphase_analysis_padded":
             # large file not yet in memory: stream it piecewise through pinned buffers (file_streaming.py);
             # the returned object holds the header, .load_data() reads the payload
             from .file_streaming import stream_channelize
             return stream_channelize(self, input_data_file.file_path, output_dir, output_file_name)
-        if input_data_file.data is None:
+        if input_data_file._data is None:
             input_data_file.load_data()
         out = self.channelize_array(input_data_file.data)
         if output_file_name is None:
@@ -140,10 +140,10 @@ class PSRFormatSynthesizer:
         return out.cpu().numpy()[:, None, :]
 
     def __call__(self, input_data_file, output_dir="./", output_file_name=None):
-        if input_data_file.data is None and _stream_it(input_data_file.file_path):
+        if input_data_file._data is None and _stream_it(input_data_file.file_path):
             from .file_streaming import stream_synthesize
             return stream_synthesize(self, input_data_file.file_path, output_dir, output_file_name)
-        if input_data_file.data is None:
+        if input_data_file._data is None:
             input_data_file.load_data()
         hdr = input_data_file.header
         os_factor = Rational.from_str(hdr["OS_FACTOR"])

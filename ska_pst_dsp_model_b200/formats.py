@@ -74,6 +74,7 @@ class DADAFile:
         self.file_path = file_path
         self._header = OrderedDict(header) if header is not None else OrderedDict(DEFAULT_HEADER)
         self._data = None
+        self._lazy = False          # set by the streaming operators: .data maps the payload on first access
         if data is not None:
             self.data = data
         elif header is None and os.path.exists(file_path) and os.path.getsize(file_path) >= 4096:
@@ -120,7 +121,24 @@ class DADAFile:
     # -- payload -------------------------------------------------------------
     @property
     def data(self):
+        if self._data is None and self._lazy:
+            self._map_payload()
         return self._data
+
+    def _map_payload(self):
+        """Results of the streaming operators live on disk only; map them (float payloads) or load them (integer
+        payloads) when a caller asks for .data, so that code written against psr_formats keeps working."""
+        hdr = read_header(self.file_path)
+        nbit, off = int(hdr["NBIT"]), int(hdr["HDR_SIZE"])
+        per = int(hdr["NCHAN"]) * int(hdr["NPOL"])
+        if int(hdr.get("NDIM", "2")) == 2 and nbit in (32, 64):
+            cdt = np.complex64 if nbit == 32 else np.complex128
+            ndat = (os.path.getsize(self.file_path) - off) // (per * np.dtype(cdt).itemsize)
+            self._header = hdr
+            self._data = np.memmap(self.file_path, dtype=cdt, mode="r", offset=off,
+                                   shape=(ndat, int(hdr["NCHAN"]), int(hdr["NPOL"])))
+        else:
+            self.load_data()
 
     @data.setter
     def data(self, arr):

@@ -162,6 +162,11 @@ class InversePlan:
     def set_scratch_bytes(self, nbytes):
         _l.check(_l.lib.pfb_inverse_set_scratch_bytes(self._h, int(nbytes)))
 
+    def reserve(self, n_dat, npol=2, ngroups=1):
+        """Size the plan's scratch for inputs of up to n_dat fine-channel samples before capturing a CUDA graph
+        (a plan is single-stream, not thread-safe, and regrows its scratch with cudaFree + cudaMalloc)."""
+        _l.check(_l.lib.pfb_inverse_reserve(self._h, int(npol), int(n_dat), int(ngroups)))
+
     def __call__(self, x, out=None, sample_offset=1):
         """sample_offset is 1-based like polyphase_synthesis.m:99."""
         _check_tensor(x, self.dtype, self.device, 3)

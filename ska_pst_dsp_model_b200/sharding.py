@@ -145,7 +145,8 @@ class ShardedRoundTrip:
         else:
             a = self.analysis
             k_int = max(0, (s.own_n - a.fl) // a.step + 1)
-            k_int = min(s.fine_n, k_int // 4 * 4)          # multiple of nu: the tail launch starts rotation-free
+            nu = a.os_factor.nu
+            k_int = min(s.fine_n, k_int // nu * nu)        # multiple of nu: the tail launch starts rotation-free
             if k_int > 0:
                 a.segment(self.local[: s.own_n], s.own0, s.fine0, k_int, out=self.chan[:k_int])
             for r in reqs:

@@ -1,0 +1,152 @@
+"""Oracle parity at the FULL sizes of BASELINE.json's configs: the complete GPU result is
+compared with the complete fp64 oracle result - every output block of every persistent CTA run, every
+overlap-save block of every time split - not a prefix.  The oracle needs 10-40 s of one host core per case.
+
+Tolerance (north star): normalised max error max|a-b| / max|b| <= 1e-5 for complex64 against the fp64 oracle."""
+import numpy as np
+import pytest
+
+from oracle import pfb_oracle as o
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+def cn(rng, shape):
+    x = np.empty(shape, dtype=np.complex64)
+    x.real = rng.standard_normal(shape, dtype=np.float32)
+    x.imag = rng.standard_normal(shape, dtype=np.float32)
+    return x
+
+
+def dev(a_pct):
+    import torch
+    a = np.ascontiguousarray(np.transpose(a_pct, (2, 1, 0)))
+    if a_pct.shape[1] == 1:
+        a = a[:, 0, :]
+    return torch.from_numpy(a).cuda()
+
+
+def host(t):
+    a = t.cpu().numpy()
+    if a.ndim == 2:
+        a = a[:, None, :]
+    return np.transpose(a, (2, 1, 0))
+
+
+def nerr(a, b):
+    return float(np.abs(a - b).max() / np.abs(b).max())
+
+
+def windowed_worst(got, ref, nwin=64):
+    """Worst normalised error over nwin equal windows along the last axis (localises a failure to a CTA run)."""
+    n = ref.shape[-1]
+    scale = np.abs(ref).max()
+    edges = np.linspace(0, n, nwin + 1).astype(int)
+    errs = [float(np.abs(got[..., a:b] - ref[..., a:b]).max() / scale) for a, b in zip(edges[:-1], edges[1:]) if b > a]
+    return max(errs), int(np.argmax(errs))
+
+
+def test_cfg2_low_round_trip_full_size(pst_taps):
+    """BASELINE configs[1]: 256 ch, OS 4/3, PST taps, Nf=256/ov=48 tukey + deripple, 2 pol x 2^24: all 87 365
+    analysis blocks (288+ persistent CTA runs of K1) and all 545 overlap-save blocks (9 time splits x 32 column
+    groups of K3) against the oracle."""
+    import torch
+    from ska_pst_dsp_model_b200 import ops
+    h = pst_taps / pst_taps.sum()
+    rng = np.random.default_rng(2024)
+    x = cn(rng, (2, 1, 1 << 24))
+    x[:, 0, 5_000_000] += 300.0                               # an impulse far from the stream edges
+    xd = dev(x)
+    ana = ops.AnalysisPlan(256, "4/3", h)
+    inv = ops.InversePlan(256, "4/3", 256, 48, "tukey", deripple_taps=h)
+    chd = ana(xd)
+    yd = inv(chd)
+    torch.cuda.synchronize()
+    ch_ref = o.polyphase_analysis(x.astype(np.complex128), h, 256, "4/3")
+    ch = host(chd)
+    assert ch.shape == ch_ref.shape == (2, 256, 87365)
+    e1, w1 = windowed_worst(ch, ch_ref, 288)
+    assert e1 < TOL, (e1, w1)
+    # the inversion is checked on the oracle's own channelized data as well as end to end
+    y_ref = o.polyphase_synthesis(ch_ref, True, 256, "4/3", h, 1, 48, o.window_tukey(256, 48))
+    y = host(yd)
+    assert y.shape == y_ref.shape == (2, 1, 545 * 30720)
+    e2, w2 = windowed_worst(y, y_ref, 545)
+    assert e2 < TOL, (e2, w2)
+    y2 = host(inv(dev(ch_ref.astype(np.complex64))))
+    e3, w3 = windowed_worst(y2, y_ref, 545)
+    assert e3 < TOL, (e3, w3)
+    print(f"cfg2 full size: analysis {e1:.2e}, round trip {e2:.2e}, inversion alone {e3:.2e}")
+
+
+def test_cfg3_mid_round_trip_full_size():
+    """BASELINE configs[2]: SKA-Mid, 4096 ch, OS 8/7, the 100 353-tap two-stage design, padded analysis,
+    Nf=512/ov=128 tukey + deripple, 2 pol x 2^24 (4681 blocks, 17 overlap-save blocks)."""
+    import torch
+    from ska_pst_dsp_model_b200 import ops
+    from ska_pst_dsp_model_b200.filters import design_pfb_fir_filter_two_stage
+    hm = design_pfb_fir_filter_two_stage(4096, 8, 7)
+    assert hm.size == 100353
+    rng = np.random.default_rng(2025)
+    x = cn(rng, (2, 1, 1 << 24))
+    xd = dev(x)
+    ana = ops.AnalysisPlan(4096, "8/7", hm, "polyphase_analysis_padded")
+    inv = ops.InversePlan(4096, "8/7", 512, 128, "tukey", deripple_taps=hm)
+    chd = ana(xd)
+    yd = inv(chd)
+    torch.cuda.synchronize()
+    ch_ref = o.polyphase_analysis_padded(x.astype(np.complex128), hm, 4096, "8/7")
+    ch = host(chd)
+    assert ch.shape == ch_ref.shape == (2, 4096, 4681)
+    e1, w1 = windowed_worst(ch, ch_ref, 64)
+    assert e1 < TOL, (e1, w1)
+    y_ref = o.polyphase_synthesis(ch_ref, True, 512, "8/7", hm, 1, 128, o.window_tukey(512, 128))
+    y = host(yd)
+    assert y.shape == y_ref.shape == (2, 1, 17 * 917504)
+    e2, w2 = windowed_worst(y, y_ref, 68)
+    assert e2 < TOL, (e2, w2)
+    print(f"cfg3 full size: analysis {e1:.2e}, round trip {e2:.2e}")
+
+
+def test_cfg1_round_trip_through_inversion(pst_taps):
+    """BASELINE configs[0] carried through the inversion: 8 ch, OS 8/7, PST taps (384 taps per arm), 2^18
+    single-pol impulse at 0.11 n; Nf=256, ov=48 -> FN_width 224 = 2^5 x 7, output FFT 1792."""
+    from ska_pst_dsp_model_b200 import ops
+    h = pst_taps / pst_taps.sum()
+    n = 1 << 18
+    x = np.zeros((1, 1, n), dtype=np.complex64)
+    x[0, 0, int(0.11 * n)] = 1.0
+    ana = ops.AnalysisPlan(8, "8/7", h)
+    inv = ops.InversePlan(8, "8/7", 256, 48, "tukey", deripple_taps=h)
+    chd = ana(dev(x))
+    ch_ref = o.polyphase_analysis(x.astype(np.complex128), h, 8, "8/7")
+    assert ch_ref.shape == (1, 8, 37010)
+    assert nerr(host(chd), ch_ref) < TOL
+    y_ref = o.polyphase_synthesis(ch_ref, True, 256, "8/7", h, 1, 48, o.window_tukey(256, 48))
+    y = host(inv(chd))
+    assert y.shape == y_ref.shape and y.shape[2] % (1792 - 2 * 336) == 0
+    assert nerr(y, y_ref) < TOL
+    # the impulse comes back at offset + fir_offset - (output_overlap - 1 + kludge) (sgcht.m:466-473; Bunton: dir -1, kludge 1)
+    peak = int(np.argmax(np.abs(y[0, 0])))
+    assert peak == int(0.11 * n) - 3072 // 2 - 336
+
+
+def test_noise_and_comb_streams_at_full_size_share_kernels(pst_taps):
+    """The bench's synthetic comb + impulse stream (bench.py synth_*) at 2^22 x 2 pol against the oracle: the
+    stream the headline number is measured on is itself oracle-checked beyond the 65 536-sample prefix."""
+    import torch
+    import bench
+    from ska_pst_dsp_model_b200 import ops
+    h = pst_taps / pst_taps.sum()
+    n = 1 << 22
+    xd = bench.synth_torch(12345 * 256, n, 2, torch.device("cuda"))
+    xh = bench.synth_numpy(12345 * 256, n, 2)
+    assert np.abs(xd.cpu().numpy() - xh).max() < 1e-6           # device and host generators agree (to fp32 rounding)
+    x = np.ascontiguousarray(xh.T[:, None, :])
+    ana = ops.AnalysisPlan(256, "4/3", h)
+    inv = ops.InversePlan(256, "4/3", 256, 48, "tukey", deripple_taps=h)
+    y = host(inv(ana(xd)))
+    ch_ref = o.polyphase_analysis(x.astype(np.complex128), h, 256, "4/3")
+    y_ref = o.polyphase_synthesis(ch_ref, True, 256, "4/3", h, 1, 48, o.window_tukey(256, 48))
+    assert y.shape == y_ref.shape and nerr(y, y_ref) < TOL

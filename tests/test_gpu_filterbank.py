@@ -57,6 +57,24 @@ def test_filterbank_rounding_options():
     assert np.all(g.real == np.round(g.real)) and np.mean(np.abs(g - r) > 0.5) < 2e-3
 
 
+def test_filterbank_rounding_ties_go_away_from_zero():
+    """Matlab round() (FilterBank.m:82): every input sits exactly on a .5 boundary, so half-to-even and
+    half-away-from-zero differ on half of the samples; oracle and product must agree to fp32 accuracy."""
+    from ska_pst_dsp_model_b200.filterbank import FilterBank
+    rng = np.random.default_rng(21)
+    h = rng.standard_normal(81) / 9
+    n = 4000
+    x = (rng.integers(-6, 6, (1, 1, n)) + 0.5 + 1j * (rng.integers(-6, 6, (1, 1, n)) + 0.5)).astype(np.complex64)
+    kw = dict(rnd_input=True, rms_input=0.0)
+    r = o.FilterBank(h, 8, "8/7", **kw).execute(x.astype(np.complex128))
+    g = host(FilterBank(h, 8, "8/7", **kw).execute(dev(x)))
+    assert g.shape == r.shape and nerr(g, r) < 1e-5
+    # and the rounding really is half-away-from-zero: the same filterbank fed the rounded input directly
+    xr = np.sign(x.real) * np.floor(np.abs(x.real) + 0.5) + 1j * np.sign(x.imag) * np.floor(np.abs(x.imag) + 0.5)
+    r2 = o.FilterBank(h, 8, "8/7").execute(xr.astype(np.complex128))
+    assert nerr(r, r2) < 1e-12
+
+
 def test_filterbank_lowcbf_first_call_flag(pst_taps):
     from ska_pst_dsp_model_b200.filterbank import FilterBank
     rng = np.random.default_rng(3)

@@ -151,3 +151,16 @@ def test_generators():
     assert len(a) == 32 and abs(f[0] - (-0.5 + 1 / 128)) < 1e-15 and abs(a[-1] - 2 ** 0.5) < 1e-15
     c = o.frequency_comb(256, a, f)
     assert c.shape == (256,)
+
+
+def test_matlab_round_ties_away_from_zero():
+    """FilterBank.m:82,112 use Matlab round(): 0.5 -> 1, -0.5 -> -1, 2.5 -> 3 (numpy would give 0, -0, 2)."""
+    z = np.array([0.5, -0.5, 1.5, 2.5, -2.5, 0.49, -3.51])
+    assert np.array_equal(o.matlab_round(z), [1, -1, 2, 3, -3, 0, -4])
+    zc = np.array([2.5 - 0.5j, -1.5 + 4.5j])
+    assert np.array_equal(o.matlab_round(zc), [3 - 1j, -2 + 5j])
+    h = np.ones(16) / 16
+    x = (np.arange(400) % 7 - 3 + 0.5).astype(np.complex128)[None, None, :]
+    a = o.FilterBank(h, 8, "8/7", rnd_input=True).execute(x)
+    b = o.FilterBank(h, 8, "8/7").execute(o.matlab_round(x))
+    assert np.array_equal(a, b)
