@@ -97,6 +97,12 @@ int pfb_inverse_execute_batched(pfb_inverse_plan* plan, const void* in_dev, void
 /* spectral (frequency-domain) taper of polyphase_synthesis.m:282 / InverseFilterBank.frequency_taper:
  * n = nchan*FN_width doubles multiplying the stitched spectrum (NULL clears it).  With a taper set
  * the inversion runs the literal-order chain (per-channel FFT -> weights -> channel IDFT -> bin IFFT). */
+/* nvec independent channelized series stored back to back, row pitch vec_rows (>= n_dat) fine samples each:
+ * in [nvec][vec_rows][nchan][npol] -> out [nvec][n_blocks*output_keep][npol].  Replaces the per-vector synthesize
+ * call of the purity sweep (python/verify/purity.py:175-177, matlab/current_performance.m:261-299); one launch per
+ * kernel for the whole batch on the SKA-Low fast path. */
+int pfb_inverse_execute_vectors(pfb_inverse_plan* plan, const void* in_dev, void* out_dev, int npol, int nvec,
+                                long long vec_rows, long long n_dat, void* stream);
 int pfb_inverse_set_spectral_taper(pfb_inverse_plan* plan, const double* taper, long long n);
 /* bytes of scratch between the two inversion kernels (default 1 GiB: the whole stream in one chunk up to ~2^25
  * samples/pol at the SKA-Low shape; longer streams are processed in chunks of whole overlap-save blocks) */
@@ -123,7 +129,9 @@ int pfb_inverse_get_profile(pfb_inverse_plan* plan, double* ms2, long long* laun
 /* ---- on-device test vectors and purity reductions (python/data_gen/generate_test_vector.py:24-71,
  *      python/verify/util.py:15-43, purity.py:154-160).
  * kind 0: time_domain_impulse(n, offset=p0, width=p1); kind 1: complex_sinusoid(n, freq=p0 [bins],
- * phase=p1 [rad], bin_offset=p2); every polarisation gets the same signal; out: [n][npol]. */
+ * phase=p1 [rad], bin_offset=p2); kind 2: the 32-tone frequency comb of matlab/FrequencyComb.m:22-46 with the
+ * amplitudes / spacing of sgcht.m:394-432 (a_k = linspace(1, sqrt 2, 32), f_k = -0.5 + 1/128 + p2 + p0/n + k/32
+ * cycles per sample, common phase p1); every polarisation gets the same signal; out: [n][npol]. */
 int pfb_generate_test_vector(int kind, void* out_dev, long long n, int npol, int dtype, double p0,
                              double p1, double p2, void* stream);
 /* same signal written to out[t * stride] only: lets the batch driver place two independent test vectors in the
@@ -141,6 +149,12 @@ int pfb_generate_test_vectors(int kind, void* out_dev, long long n, int nvec, in
  * reference a, may be NULL) and writes out[0..7] = sum|b-a|, max|b-a|, sum|b|^2, largest |b|^2,
  * second largest |b|^2, argmax, sum|b|, n. */
 int pfb_purity_metrics(const void* args_dev, int nvec, int dtype, void* stream);
+/* Spectra of npairs dual-pol series of nfft = 98304 (= 2 x 192 x 256, the purity report's fft_size for SKA-Low:
+ * python/verify/purity.py:84,150,236-263; matlab/DomainPerformance.m:58-100) points each: in [pair][pitch][2] complex64
+ * (pitch in samples), scratch and out [pair][nfft][2].  The bins are stored transposed, out[k1][k2] = X[k1 + 24 k2];
+ * the report's reductions do not depend on the order.  Other lengths: PFB_ERR_UNSUPPORTED. */
+int pfb_spectrum_vectors(const void* in_dev, long long pitch, void* scratch_dev, void* out_dev, int npairs,
+                         long long nfft, void* stream);
 
 /* kernels launched by this library since load (bench.py "gpu_launches") */
 long long pfb_launch_count(void);

@@ -691,12 +691,13 @@ static int launch_chan_idft(pfb_inverse_plan* p, const void* in, void* out, int 
 
 template <typename T>
 static int launch_resample(pfb_inverse_plan* p, const void* v, void* out, int npol, long long nblk, cudaStream_t st,
-                           int G = 1, bool grouped = false, long long rows_cap = 0) {
+                           int G = 1, bool grouped = false, long long rows_cap = 0, long long vec_rows = 0,
+                           long long vec_blocks = 0) {
   if (nblk <= 0) return PFB_OK;
   const int tok = p->prof_begin(1, st);
   if (p->low_fast) {
     bool done = false;
-    int rc = low_resample_launch<T>(p->d_low, v, out, npol, nblk, G, st, &done, grouped, rows_cap);
+    int rc = low_resample_launch<T>(p->d_low, v, out, npol, nblk, G, st, &done, grouped, rows_cap, vec_rows, vec_blocks);
     if (rc) return fail(PFB_ERR_CUDA, "pfb_resample_low launch: %s", cudaGetErrorString((cudaError_t)rc));
     if (done) { p->prof_end(tok, st); return check_launch("pfb_resample_low"); }
   }
@@ -771,6 +772,54 @@ static int inverse_run(pfb_inverse_plan* p, const void* in, void* out, int npol,
     int rc = launch_chan_idft<T>(p, src, p->d_scratch, npol, rows * G, st, ws);  // every (tau, group) is one row
     if (rc) return rc;
     rc = launch_resample<T>(p, p->d_scratch, dst, npol, nb, st, G, ws, rows);
+    if (rc) return rc;
+  }
+  return PFB_OK;
+}
+
+// A batch of nvec independent channelized series stored back to back (row pitch vec_rows >= n_dat fine samples each):
+// the purity sweep (python/verify/purity.py:165-207 runs one synthesize call per test vector).  On the SKA-Low
+// dual-pol fast path the whole batch is ONE channel-IDFT launch over all rows and ONE resample launch in which every
+// vector is a time split of the grid; other shapes run vector by vector.
+template <typename T>
+static int inverse_run_vectors(pfb_inverse_plan* p, const void* in, void* out, int npol, int nvec, long long vec_rows,
+                               long long n_dat, cudaStream_t st) {
+  const long long nblocks = pfb_inverse_nblocks(p, n_dat);
+  if (nblocks <= 0 || nvec <= 0) return PFB_OK;
+  const long long rowlen = (long long)p->nchan * npol;
+  const long long rowbytes = rowlen * (long long)sizeof(Cx<T>);
+  const long long out_per = nblocks * p->keep2 * rowlen;                 // output elements per vector
+  const bool ws = p->low_fast && p->ws_fast && std::is_same<T, float>::value && low_ws_ok(p->d_low, npol, 1, in, out) &&
+                  ((vec_rows * rowbytes) % 16 == 0);
+  if (!ws) {
+    for (int v = 0; v < nvec; ++v) {
+      int rc = inverse_run<T>(p, reinterpret_cast<const Cx<T>*>(in) + (long long)v * vec_rows * rowlen,
+                              reinterpret_cast<Cx<T>*>(out) + (long long)v * out_per, npol, n_dat, st);
+      if (rc) return rc;
+    }
+    return PFB_OK;
+  }
+  long long vb = p->scratch_bytes / (vec_rows * rowbytes);                // vectors per launch pair
+  if (vb < 1) vb = 1;
+  if (vb > nvec) vb = nvec;
+  const size_t need = (size_t)(vb * vec_rows * rowbytes);
+  if (need > p->scratch_cap) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(st, &cs);
+    if (cs != cudaStreamCaptureStatusNone)
+      return fail(PFB_ERR_ARG, "inversion scratch must grow during stream capture: run the batch once (or reserve) first");
+    if (p->d_scratch) CU(cudaFree(p->d_scratch));
+    p->d_scratch = nullptr; p->scratch_cap = 0;
+    CU(cudaMalloc(&p->d_scratch, need));
+    p->scratch_cap = need;
+  }
+  for (long long v0 = 0; v0 < nvec; v0 += vb) {
+    const long long nv = (nvec - v0 < vb) ? nvec - v0 : vb;
+    const Cx<T>* src = reinterpret_cast<const Cx<T>*>(in) + v0 * vec_rows * rowlen;
+    Cx<T>* dst = reinterpret_cast<Cx<T>*>(out) + v0 * out_per;
+    int rc = launch_chan_idft<T>(p, src, p->d_scratch, npol, nv * vec_rows, st, true);
+    if (rc) return rc;
+    rc = launch_resample<T>(p, p->d_scratch, dst, npol, nv * nblocks, st, 1, true, nv * vec_rows, vec_rows, nblocks);
     if (rc) return rc;
   }
   return PFB_OK;
@@ -942,6 +991,20 @@ int pfb_inverse_execute_batched(pfb_inverse_plan* p, const void* in_dev, void* o
                                    : inverse_run<double>(p, in_dev, out_dev, npol, n_dat, st, ngroups);
 }
 
+int pfb_inverse_execute_vectors(pfb_inverse_plan* p, const void* in_dev, void* out_dev, int npol, int nvec,
+                                long long vec_rows, long long n_dat, void* stream) {
+  if (!p) return fail(PFB_ERR_ARG, "null plan");
+  if (npol < 1 || npol > 2 || nvec < 0 || n_dat < 0 || vec_rows < n_dat)
+    return fail(PFB_ERR_ARG, "pfb_inverse_execute_vectors: bad argument (need vec_rows >= n_dat)");
+  if (p->spectral) return fail(PFB_ERR_UNSUPPORTED, "vector batches with a spectral taper are not implemented");
+  if (nvec == 0 || pfb_inverse_nblocks(p, n_dat) <= 0) return PFB_OK;
+  if (!in_dev || !out_dev) return fail(PFB_ERR_ARG, "null pointer");
+  CU(cudaSetDevice(p->device));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  return p->dtype == PFB_DTYPE_C64 ? inverse_run_vectors<float>(p, in_dev, out_dev, npol, nvec, vec_rows, n_dat, st)
+                                   : inverse_run_vectors<double>(p, in_dev, out_dev, npol, nvec, vec_rows, n_dat, st);
+}
+
 int pfb_inverse_execute_stage(pfb_inverse_plan* p, int stage, const void* in_dev, void* out_dev, int npol,
                               long long n_dat, void* stream) {
   if (!p || !in_dev || !out_dev) return fail(PFB_ERR_ARG, "null pointer");
@@ -963,7 +1026,7 @@ int pfb_inverse_execute_stage(pfb_inverse_plan* p, int stage, const void* in_dev
 // test vectors + purity reductions on device
 static int generate_run(int kind, void* out_dev, long long n, int npol, long long stride, int dtype, double p0, double p1,
                         double p2, void* stream) {
-  if (!out_dev || n < 0 || npol < 1 || stride < npol || (kind != 0 && kind != 1))
+  if (!out_dev || n < 0 || npol < 1 || stride < npol || kind < 0 || kind > 2)
     return fail(PFB_ERR_ARG, "pfb_generate_test_vector: bad argument");
   if (n == 0) return PFB_OK;
   GenArgs a;
@@ -989,7 +1052,7 @@ int pfb_generate_test_vector_strided(int kind, void* out_dev, long long n, long 
 
 int pfb_generate_test_vectors(int kind, void* out_dev, long long n, int nvec, int group, long long group_stride, int dtype,
                               const double* params_dev, void* stream) {
-  if (!out_dev || !params_dev || n < 0 || nvec < 0 || group < 1 || (kind != 0 && kind != 1))
+  if (!out_dev || !params_dev || n < 0 || nvec < 0 || group < 1 || kind < 0 || kind > 2)
     return fail(PFB_ERR_ARG, "pfb_generate_test_vectors: bad argument");
   if (n == 0 || nvec == 0) return PFB_OK;
   if (nvec > 65535) return fail(PFB_ERR_ARG, "pfb_generate_test_vectors: at most 65535 vectors per call");
@@ -1003,6 +1066,44 @@ int pfb_generate_test_vectors(int kind, void* out_dev, long long n, int nvec, in
   else if (dtype == PFB_DTYPE_C128) pfb_generate_batch_kernel<double><<<grid, 256, 0, st>>>(a);
   else return fail(PFB_ERR_ARG, "dtype must be 0 (c64) or 1 (c128)");
   return check_launch("pfb_generate_batch_kernel");
+}
+
+// 98 304-point spectra of npairs dual-pol series (four-step: pfb_spectrum24_step1 + pfb_rowfft4096)
+int pfb_spectrum_vectors(const void* in_dev, long long pitch, void* scratch_dev, void* out_dev, int npairs, long long nfft,
+                         void* stream) {
+  if (npairs < 0 || pitch < 0) return fail(PFB_ERR_ARG, "pfb_spectrum_vectors: bad argument");
+  if (nfft != 24 * 4096) return fail(PFB_ERR_UNSUPPORTED, "pfb_spectrum_vectors: only nfft = 98304 = 24 x 4096 is implemented (got %lld)", nfft);
+  if (npairs == 0) return PFB_OK;
+  if (!in_dev || !scratch_dev || !out_dev) return fail(PFB_ERR_ARG, "null pointer");
+  if ((uintptr_t)in_dev % 16 || (uintptr_t)scratch_dev % 16 || (uintptr_t)out_dev % 16)
+    return fail(PFB_ERR_ARG, "pfb_spectrum_vectors: buffers must be 16-byte aligned");
+  if (npairs > 65535) return fail(PFB_ERR_ARG, "pfb_spectrum_vectors: at most 65535 pairs per call");
+  // 4096-point twiddle table, one per device (tiny, lives for the process)
+  static const float2* tw_dev[64] = {nullptr};
+  int dev = 0;
+  CU(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) return fail(PFB_ERR_ARG, "device index out of range");
+  if (!tw_dev[dev]) {
+    std::vector<float2> tw = low::unit_table(4096, -1);
+    void* d = nullptr;
+    CU(cudaMalloc(&d, tw.size() * sizeof(float2)));
+    CU(cudaMemcpy(d, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice));
+    tw_dev[dev] = reinterpret_cast<const float2*>(d);
+  }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  mid::SpecArgs sa;
+  sa.in = reinterpret_cast<const float4*>(in_dev);
+  sa.s1 = reinterpret_cast<float4*>(scratch_dev);
+  sa.pitch = pitch;
+  mid::pfb_spectrum24_step1<<<dim3(16, (unsigned)npairs), 256, 0, st>>>(sa);
+  int rc = check_launch("pfb_spectrum24_step1");
+  if (rc) return rc;
+  mid::RowFftArgs m;
+  memset(&m, 0, sizeof(m));
+  m.in = scratch_dev; m.out = out_dev; m.tw = tw_dev[dev]; m.jmap = nullptr; m.nrows = 24ll * npairs;
+  rc = mid::rowfft4096_launch<-1, false>(m, st);
+  if (rc) return fail(PFB_ERR_CUDA, "pfb_rowfft4096 launch: %s", cudaGetErrorString((cudaError_t)rc));
+  return check_launch("pfb_rowfft4096");
 }
 
 int pfb_purity_metrics(const void* args_dev, int nvec, int dtype, void* stream) {

@@ -87,6 +87,8 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// (try_wait already suspends the warp in hardware for a bounded time; a longer suspend-time hint was measured
+//  in round 2 and made all three kernels slower: K1 +5 %, K2 +17 %, K3 +2 %)
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   asm volatile(
       "{\n"
@@ -240,13 +242,18 @@ __global__ void __launch_bounds__(64 * NPOL, NPOL == 2 ? 2 : 4) pfb_analysis_low
       z[2] = z[2] * tw[1];
       z[3] = z[3] * tw[2];
 #pragma unroll
-      for (int o = 0; o < 4; ++o) ex[(size_t)((j * NPOL + pol) * 4 + o) * kExStride + r] = z[o];
+      // exchange row T = ((j >> 1) * NPOL + pol) * 8 + (j & 1) * 4 + o: the two polarisations of a warp's 64-bit stores
+      // sit 8 rows = 8 (mod 16) units apart, i.e. on the other half of the banks (the natural numbering (j, pol, o)
+      // put them 4 rows apart: 2-way conflicts on half of the units, 34 % of K1's shared wavefronts in ncu r1d)
+#pragma unroll
+      for (int o = 0; o < 4; ++o)
+        ex[(size_t)((((j >> 1) * NPOL + pol) * 8 + (j & 1) * 4) + o) * kExStride + r] = z[o];
     }
     __syncthreads();
     {
       // one 64-point FFT per thread (task = block j, pol, o), two radix-8 passes over the
       // thread's private row in shared memory (the 48-sample window keeps the registers)
-      const int o = tid & 3, tp = (tid >> 2) % NPOL, tj = tid / (4 * NPOL);
+      const int o = tid & 3, tp = (tid >> 3) % NPOL, tj = 2 * (tid / (8 * NPOL)) + ((tid >> 2) & 1);   // row T = tid
       C* row = ex + (size_t)tid * kExStride;
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
@@ -620,6 +627,8 @@ struct WsArgs {
   const float2* tw256;
   const float2* tw192;
   long long rows_cap;   // rows per group in the scratch
+  long long split_rows; // scratch rows between the starts of consecutive time splits (stream: per * 160; batch of
+                        // independent vectors: the row pitch of one vector)
   int nchan;            // output row pitch in t1
   int nblk, nsplit;
 };
@@ -675,7 +684,7 @@ __global__ void __launch_bounds__(32 * (kWsWarps + 1), 2)
   }
   __syncthreads();
 
-  const char* vgrp = a.v + ((long long)g * a.rows_cap + (long long)n_begin * kWsStepRows) * kWsRowBytes;
+  const char* vgrp = a.v + ((long long)g * a.rows_cap + (long long)sp * a.split_rows) * kWsRowBytes;
   // load k: k = 0 is the 96-row head of the first block, k >= 1 the 160 new rows of block k - 1
   auto issue = [&](int k) {
     const uint32_t bytes = (k == 0 ? 96u : 160u) * kWsRowBytes;
@@ -1068,14 +1077,15 @@ inline long long low_resample_nsplit(const void* d_low, int npol, int groups_b =
 
 template <typename T>
 int low_resample_launch(const void* d_low, const void* v, void* out, int npol, long long nblk, int groups_b, cudaStream_t st, bool* done,
-                        bool grouped = false, long long rows_cap = 0) {
+                        bool grouped = false, long long rows_cap = 0, long long vec_rows = 0, long long vec_blocks = 0) {
   *done = false;
   return 0;
 }
 
 template <>
 inline int low_resample_launch<float>(const void* d_low, const void* v, void* out, int npol, long long nblk,
-                                      int groups_b, cudaStream_t st, bool* done, bool grouped, long long rows_cap) {
+                                      int groups_b, cudaStream_t st, bool* done, bool grouped, long long rows_cap,
+                                      long long vec_rows, long long vec_blocks) {
   *done = false;
   const low::LowInverse* h = reinterpret_cast<const low::LowInverse*>(d_low);
   if (nblk > 2000000000ll) return grouped ? (int)cudaErrorInvalidValue : 0;
@@ -1092,7 +1102,9 @@ inline int low_resample_launch<float>(const void* d_low, const void* v, void* ou
     long long ns = ((long long)sms * 2) / groups;     // one resident wave, 2 CTAs per SM
     if (ns > nblk) ns = nblk;
     if (ns < 1) ns = 1;
+    if (vec_blocks > 0) ns = nblk / vec_blocks;       // independent vectors: one time split per vector
     w.nsplit = (int)ns;
+    w.split_rows = vec_blocks > 0 ? vec_rows : ((nblk + ns - 1) / ns) * (long long)low::kWsStepRows;
     // tensor map of the output rows: [nblk * 120 rows][nchan * 4 fp32], box = 120 rows x 128 B
     typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,

@@ -140,6 +140,48 @@ inline int rowfft4096_launch(const RowFftArgs& a, cudaStream_t st) {
 }
 
 // ---------------------------------------------------------------------------
+// Long power-of-two-times-24 spectra of dual-pol series (the 2 * block_size = 98 304 = 24 x 4096 point transforms of
+// the purity report, python/verify/purity.py:150,236-263, DomainPerformance.m:58-100): four-step FFT,
+//   X[k1 + 24 k2] = sum_n2 W4096^(n2 k2) * [ W_N^(n2 k1) * sum_n1 x[4096 n1 + n2] W24^(n1 k1) ],
+// step 1 (this kernel): the 24-point DFTs across n1 (3 x 8 in registers) and the twiddle, rows written as
+// [k1][n2]; step 2: pfb_rowfft4096 over the 24 rows.  The result is stored transposed, spec[k1][k2] = X[k1 + 24 k2]:
+// the report's reductions (sums, maxima, |b - a|) do not depend on the bin order.
+struct SpecArgs {
+  const float4* in;       // [pair][pitch] (pol0.re, pol0.im, pol1.re, pol1.im)
+  float4* s1;             // [pair][24][4096]
+  long long pitch;        // float4 units between consecutive pairs
+};
+
+__global__ void __launch_bounds__(256) pfb_spectrum24_step1(const SpecArgs a) {
+  constexpr int M = 24, N = M * 4096;
+  const int n2 = blockIdx.x * 256 + threadIdx.x;
+  const long long pair = blockIdx.y;
+  const float4* p = a.in + pair * a.pitch + n2;
+  C x0[M], x1[M];
+#pragma unroll
+  for (int n1 = 0; n1 < M; ++n1) {
+    const float4 v = __ldg(p + (long long)n1 * 4096);
+    x0[n1] = mk<float>(v.x, v.y);
+    x1[n1] = mk<float>(v.z, v.w);
+  }
+  fft_reg<3, 8, -1>(x0);
+  fft_reg<3, 8, -1>(x1);
+  float4* q = a.s1 + pair * (long long)N + n2;
+#pragma unroll
+  for (int k1 = 0; k1 < M; ++k1) {
+    C u0 = x0[slot<3, 8>(k1)], u1 = x1[slot<3, 8>(k1)];
+    if (k1) {
+      float sn, cs;
+      sincospif(-2.0f * (float)((n2 * k1) % N) / (float)N, &sn, &cs);      // n2 k1 < N: exact integer in fp32
+      const C w = mk<float>(cs, sn);
+      u0 = u0 * w;
+      u1 = u1 * w;
+    }
+    q[(long long)k1 * 4096] = make_float4(u0.x, u0.y, u1.x, u1.y);
+  }
+}
+
+// ---------------------------------------------------------------------------
 // Sliding-window polyphase FIR with the block phases sharing their input (fp32, dual-pol, long filters).
 //
 // nu*S = de*N, so block k = k0 + nu*i of output arm j reads the sub-stream of SAMPLE arm

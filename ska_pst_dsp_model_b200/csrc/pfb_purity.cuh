@@ -12,18 +12,53 @@ struct GenArgs {
   void* out;            // [n][stride] complex; the first npol entries of every row are written
   long long n;
   long long stride;
-  int npol, kind;       // 0 impulse, 1 tone
-  double p0, p1, p2;    // impulse: offset, width;  tone: frequency (bins), phase (rad), bin offset
+  int npol, kind;       // 0 impulse, 1 tone, 2 frequency comb
+  double p0, p1, p2;    // impulse: offset, width;  tone: frequency (bins), phase (rad), bin offset;
+                        // comb: frequency shift (bins of n), phase (rad), extra offset (cycles/sample)
 };
+
+// Frequency comb of matlab/FrequencyComb.m:22-46 with the parameters of sgcht.m:394-432: 32 tones, amplitudes
+// linspace(1, sqrt 2, 32), f_k = fmin + k/32 cycles per sample, fmin = -0.5 + 1/128 (+ offsets).  The tones sit 1/32
+// apart, so x[t] = exp(2 pi i f0 t) * P[t mod 32] with P[m] = sum_k a_k exp(2 pi i k m / 32): one sincos per sample.
+__device__ __forceinline__ void comb_table(double* pr, double* pi) {      // called by threads 0..31, fills P[32]
+  const int m = threadIdx.x;
+  double sr = 0, si = 0;
+  for (int k = 0; k < 32; ++k) {
+    const double amp = 1.0 + (1.4142135623730951 - 1.0) * (double)k / 31.0;
+    double sn, cs;
+    sincospi(2.0 * (double)((k * m) & 31) / 32.0, &sn, &cs);
+    sr += amp * cs;
+    si += amp * sn;
+  }
+  pr[m] = sr;
+  pi[m] = si;
+}
+template <typename T>
+__device__ __forceinline__ Cx<T> comb_sample(long long t, long long n, double p0, double p1, double p2, const double* pr,
+                                             const double* pi) {
+  const double f0 = -0.5 + 1.0 / 128.0 + p2 + p0 / (double)n;
+  const double cyc = f0 * (double)t;
+  double sn, cs;
+  sincos(2.0 * 3.14159265358979323846 * (cyc - floor(cyc)) + p1, &sn, &cs);
+  const int m = (int)(t & 31);
+  return mk<T>((T)(cs * pr[m] - sn * pi[m]), (T)(cs * pi[m] + sn * pr[m]));
+}
 
 template <typename T>
 __global__ void __launch_bounds__(256) pfb_generate_kernel(const GenArgs a) {
+  __shared__ double comb_r[32], comb_i[32];
+  if (a.kind == 2) {
+    if (threadIdx.x < 32) comb_table(comb_r, comb_i);
+    __syncthreads();
+  }
   Cx<T>* out = reinterpret_cast<Cx<T>*>(a.out);
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < a.n; t += (long long)gridDim.x * blockDim.x) {
     Cx<T> v = mk<T>((T)0, (T)0);
     if (a.kind == 0) {
       const long long o = (long long)a.p0, w = (long long)a.p1;
       if (t >= o && t < o + w) v.x = (T)1;
+    } else if (a.kind == 2) {
+      v = comb_sample<T>(t, a.n, a.p0, a.p1, a.p2, comb_r, comb_i);
     } else {
       // exp(i (2 pi (f + bin_offset) t / n + phase)), evaluated in double like numpy
       const double cyc = (a.p0 + a.p2) * (double)t / (double)a.n;
@@ -50,6 +85,11 @@ struct GenBatchArgs {
 
 template <typename T>
 __global__ void __launch_bounds__(256) pfb_generate_batch_kernel(const GenBatchArgs a) {
+  __shared__ double comb_r[32], comb_i[32];
+  if (a.kind == 2) {
+    if (threadIdx.x < 32) comb_table(comb_r, comb_i);
+    __syncthreads();
+  }
   const int v = blockIdx.y;
   const double p0 = a.params[3 * v], p1 = a.params[3 * v + 1], p2 = a.params[3 * v + 2];
   Cx<T>* out = reinterpret_cast<Cx<T>*>(a.out) + (long long)(v / a.group) * a.group_stride + (v % a.group);
@@ -58,6 +98,8 @@ __global__ void __launch_bounds__(256) pfb_generate_batch_kernel(const GenBatchA
     if (a.kind == 0) {
       const long long o = (long long)p0, w = (long long)p1;
       if (t >= o && t < o + w) val.x = (T)1;
+    } else if (a.kind == 2) {
+      val = comb_sample<T>(t, a.n, p0, p1, p2, comb_r, comb_i);
     } else {
       const double cyc = (p0 + p2) * (double)t / (double)a.n;
       const double ang = 2.0 * 3.14159265358979323846 * (cyc - floor(cyc)) + p1;

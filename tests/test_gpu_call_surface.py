@@ -121,16 +121,18 @@ def test_batch_purity_matches_file_driver(tmp_path, pst_taps):
     t.time_domain_args["offset"], t.freq_domain_args["frequency"] = offs, freqs
     t.temporal_purity()
     t.spectral_purity()
-    bp = BatchPurity("4/3", 256, 48, "tukey", True, 256, h, 3, vectors_per_batch=2)
+    # the file driver reads the deripple taps back from the channelized file's COEFF_0 key (%0.6E, synthesize.m:83-85 /
+    # add_fir_filter_to_header.m:14): give the device driver the same rounded taps so that both compute the same thing
+    h_hdr = np.array([float("%0.6E" % c) for c in h])
+    bp = BatchPurity("4/3", 256, 48, "tukey", True, 256, h, 3, vectors_per_batch=2, deripple_taps=h_hdr)
     assert bp.total_sample_shift == t.total_sample_shift and bp.n_samples == t.n_samples
     got_t, got_f = bp.temporal(offs), bp.spectral(freqs)
     for key, got in (("test_time_domain_impulse", got_t), ("test_complex_sinusoid", got_f)):
         for r, g in zip(t.report[key], got):
             assert r["arg"] == g["arg"]
             assert abs(r["total_diff"] - g["total_diff"]) <= 2e-3 * abs(r["total_diff"]) + 1e-6
-            # the file driver reads taps back from COEFF_0 (%0.6E) for the deripple: dB values agree to a fraction of a dB
             for k in ("max_spurious_power", "total_spurious_power", "mean_spurious_power"):
-                assert abs(r[k] - g[k]) < 1.0, (key, k, r[k], g[k])
+                assert abs(r[k] - g[k]) < 0.05, (key, k, r[k], g[k])
             assert g["max_spurious_power"] < -60
 
 
