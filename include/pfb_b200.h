@@ -149,6 +149,12 @@ int pfb_generate_test_vectors(int kind, void* out_dev, long long n, int nvec, in
  * reference a, may be NULL) and writes out[0..7] = sum|b-a|, max|b-a|, sum|b|^2, largest |b|^2,
  * second largest |b|^2, argmax, sum|b|, n. */
 int pfb_purity_metrics(const void* args_dev, int nvec, int dtype, void* stream);
+/* Pair form for series that carry two independent vectors in the polarisation slots of one [n][2] complex64 stream
+ * (the batched sweep): records {const void* a; const void* b; long long n; double scale_b; double* out0; double* out1;}
+ * (48 bytes); out0 / out1 get the 8 numbers above for slot 0 / slot 1.  nparts CTAs share a record: part y reduces
+ * elements [n y / nparts, n (y+1) / nparts) and writes its 8 numbers at out + 8 y (out0 / out1 hold nparts rows);
+ * the caller merges the rows. */
+int pfb_purity_metrics_pairs(const void* args_dev, int npairs, int nparts, void* stream);
 /* Spectra of npairs dual-pol series of nfft = 98304 (= 2 x 192 x 256, the purity report's fft_size for SKA-Low:
  * python/verify/purity.py:84,150,236-263; matlab/DomainPerformance.m:58-100) points each: in [pair][pitch][2] complex64
  * (pitch in samples), scratch and out [pair][nfft][2].  The bins are stored transposed, out[k1][k2] = X[k1 + 24 k2];

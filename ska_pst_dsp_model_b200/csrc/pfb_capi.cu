@@ -1059,8 +1059,9 @@ int pfb_generate_test_vectors(int kind, void* out_dev, long long n, int nvec, in
   GenBatchArgs a;
   a.out = out_dev; a.n = n; a.group = group; a.group_stride = group_stride; a.kind = kind; a.params = params_dev;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  long long gx = (n + 255) / 256;
-  if (gx > 148 * 4) gx = 148 * 4;
+  long long gx = kind == 0 ? (n + 255) / 256 : (n + kGenSpan - 1) / kGenSpan;   // tones / combs: one CTA per 65 536-sample span
+  const long long cap = nvec >= 148 ? 8 : 148 * 4;
+  if (gx > cap) gx = cap;
   const dim3 grid((unsigned)gx, (unsigned)nvec);
   if (dtype == PFB_DTYPE_C64) pfb_generate_batch_kernel<float><<<grid, 256, 0, st>>>(a);
   else if (dtype == PFB_DTYPE_C128) pfb_generate_batch_kernel<double><<<grid, 256, 0, st>>>(a);
@@ -1149,4 +1150,12 @@ int pfb_pack_payload(const void* in_dev, void* out_dev, long long nvalues, int n
   else if (dtype == PFB_DTYPE_C64) pfb_pack_kernel<float, short><<<(unsigned)grid, 256, 0, st>>>((const float*)in_dev, (short*)out_dev, nvalues, (float)scale);
   else pfb_pack_kernel<double, short><<<(unsigned)grid, 256, 0, st>>>((const double*)in_dev, (short*)out_dev, nvalues, scale);
   return check_launch("pfb_pack_kernel");
+}
+
+int pfb_purity_metrics_pairs(const void* args_dev, int npairs, int nparts, void* stream) {
+  if (!args_dev || npairs < 0 || nparts < 1 || nparts > 64) return fail(PFB_ERR_ARG, "pfb_purity_metrics_pairs: bad argument");
+  if (npairs == 0) return PFB_OK;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  pfb_metrics_pair_kernel<<<dim3((unsigned)npairs, (unsigned)nparts), 1024, 0, st>>>(reinterpret_cast<const MetricsPairArgs*>(args_dev));
+  return check_launch("pfb_metrics_pair_kernel");
 }

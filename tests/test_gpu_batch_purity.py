@@ -60,7 +60,7 @@ def test_batched_chunk_equals_per_vector_oracle(pst_taps, use_graph):
         d = np.abs(ref[: bp.n_cmp] - a)
         assert abs(rep[i]["total_diff"] - d.sum()) <= 2e-3 * d.sum() + 1e-4
     # --- tones
-    freqs = np.array([3, 300, 49152 * 3 // 2, 147455])
+    freqs = np.array([3, 300, 49152 * 3 // 2, 147453])      # multiples of blocks = 3: whole cycles in fft_size (purity.py:96-99)
     rep_f = bp.spectral(freqs)
     y = bp.y.cpu().numpy()
     for i, f in enumerate(freqs):

@@ -183,3 +183,18 @@ def test_host_round_trip_ramped_segments_tile_the_stream():
         assert sum(s.out_n for s in segs) == sum(c.out_n for c in cuts)
     ramped = HostRoundTrip._ramp(cuts, 8)
     assert ramped[0].out_n < ramped[len(ramped) // 2].out_n and ramped[-1].out_n < ramped[len(ramped) // 2].out_n
+
+
+def test_purity_partial_reductions_merge():
+    """batch._merge_parts: the per-CTA partial rows of pfb_purity_metrics_pairs merge into the whole-series numbers."""
+    from ska_pst_dsp_model_b200.batch import NPARTS, _merge_parts
+    rng = np.random.default_rng(0)
+    p = rng.random(1001)
+    m = np.zeros((2, 3, NPARTS, 8))
+    for k, ix in enumerate(np.array_split(np.arange(p.size), NPARTS)):
+        v = p[ix]
+        o = np.argsort(v)
+        m[1, 2, k] = [v.sum(), v.max(), v.sum(), v[o[-1]], v[o[-2]], ix[o[-1]], np.sqrt(v).sum(), len(ix)]
+    r = _merge_parts(m)[1, 2]
+    o = np.argsort(p)
+    assert np.allclose(r, [p.sum(), p.max(), p.sum(), p[o[-1]], p[o[-2]], o[-1], np.sqrt(p).sum(), p.size])

@@ -17,10 +17,11 @@ rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE",
 torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
 if world > 1:
     dist.init_process_group("nccl")
-nvec = int(os.environ.get("NVEC", "8192"))          # per kind: nvec impulses + nvec tones in total
+VB = 128
+nvec = int(os.environ.get("NVEC", str(VB * 8 * 8)))   # per kind (impulse, tone, comb): whole chunks on 1..8 GPUs
 h = load_pst_taps(normalise=True)
-bp = BatchPurity("4/3", 256, 48, "tukey", True, 256, h, 3, vectors_per_batch=32)
-bp.sweep(64 * world, 3, rank, world)                # warm-up: graphs for the chunk size
+bp = BatchPurity("4/3", 256, 48, "tukey", True, 256, h, 3, vectors_per_batch=VB)
+bp.sweep(VB * world, 3, rank, world)                # warm-up: scratch sized, graphs for the chunk size captured
 torch.cuda.synchronize()
 if world > 1:
     dist.barrier()
@@ -33,9 +34,9 @@ dt = time.time() - t0
 rep = gather_reports(rep, world)
 if rank == 0:
     n = sum(len(v) for v in rep.values())
-    worst_t = max(r["max_spurious_power"] for r in rep["test_time_domain_impulse"][:-1])
+    worst_t = max(r["max_spurious_power"] for r in rep["test_time_domain_impulse"] if 10752 < r["arg"] < 120000)
     worst_f = max(r["max_spurious_power"] for r in rep["test_complex_sinusoid"])
-    print(json.dumps({"workload": "batched purity sweep (impulse + tone), 147456-sample vectors, SKA-Low PST round trip",
+    print(json.dumps({"workload": "batched purity sweep (impulse + tone + comb thirds), 147456-sample vectors, SKA-Low PST round trip",
                       "n_gpus": world, "vectors": n, "seconds": dt, "vectors_per_s": n / dt,
                       "Msamples_s": n * 147456 / dt / 1e6, "worst_max_spurious_dB_time": worst_t,
                       "worst_max_spurious_dB_freq": worst_f}))
