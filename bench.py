@@ -39,13 +39,14 @@ METRIC = "input Msamples/s (PFB analysis + inversion round trip)"
 UNIT = "Msamples/s"
 
 
-def workload_config(log2n, world):
+def workload_config(log2n, world, halo=None):
     return {
         "workload": f"SKA-Low PST round trip: {NCHAN} ch, OS {OS}, 3072-tap PST filter, Nf={NFFT}, overlap={OVERLAP}, "
                     f"tukey+deripple, {NPOL} pol x 2^{log2n} complex64 samples per GPU",
         "channels": NCHAN, "os_factor": OS, "fir_taps": 3072, "input_fft_length": NFFT, "input_overlap": OVERLAP,
         "n_pol": NPOL, "samples_per_pol_per_gpu": 1 << log2n, "global_samples_per_pol": world << log2n,
         "parallelism": f"time-shard x{world}" if world > 1 else "single GPU",
+        "halo": halo,
         "l2": "inputs (256 MiB/GPU) and outputs larger than the 126 MB L2; no flush needed",
     }
 
@@ -324,8 +325,10 @@ def run_b200(args):
     log2n = args.log2_samples
     n_global = world << log2n
     taps = load_pst_taps(normalise=True)
-    shard = plan_time_shards(n_global, world, NCHAN, OS, 3072, NFFT, OVERLAP)[rank]
-    rt = ShardedRoundTrip(shard, NCHAN, OS, taps, NFFT, OVERLAP, "tukey", True, NPOL, torch.complex64, dev)
+    shards = plan_time_shards(n_global, world, NCHAN, OS, 3072, NFFT, OVERLAP)
+    shard = shards[rank]
+    rt = ShardedRoundTrip(shard, NCHAN, OS, taps, NFFT, OVERLAP, "tukey", True, NPOL, torch.complex64, dev,
+                          halo=args.halo, shards=shards)
     if args.scratch_mib:
         rt.inverse.set_scratch_bytes(args.scratch_mib << 20)
     rt.load_owned(synth_torch(shard.own0, shard.own_n, NPOL, dev))
@@ -451,6 +454,10 @@ def run_b200(args):
     from ska_pst_dsp_model_b200.streaming import HostRoundTrip
     Ke = max(1, min(K, args.e2e_steps))
     x_host = torch.empty((shard.need_n, NPOL), dtype=torch.complex64).pin_memory()
+    if world > 1:           # (setup, untimed) the host buffer holds the halo too: fetch it once, whatever the device halo mode
+        from ska_pst_dsp_model_b200.sharding import exchange_halo
+        exchange_halo(torch.view_as_real(rt.local), shard)
+        torch.cuda.synchronize()
     x_host.copy_(rt.local[: shard.need_n])
     del rt.chan
     hrt = HostRoundTrip(shard.need_n, NCHAN, OS, taps, NFFT, OVERLAP, "tukey", True, NPOL, nseg=args.e2e_segments,
@@ -526,7 +533,7 @@ def run_b200(args):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic", "config": workload_config(log2n, world), "clocks": clocks, "e2e": e2e,
+        "data": "synthetic", "config": workload_config(log2n, world, rt.halo_mode if world > 1 else None), "clocks": clocks, "e2e": e2e,
         "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline, "kernels": kernels,
         "pipeline": pipeline, "sustained": sustained, "round_trip_max_err": rt_err,
         "other_configs": other,
@@ -724,6 +731,9 @@ def main():
     ap.add_argument("--e2e-segments", type=int, default=8, help="base segment count of the host round trip (ramped head and tail add a few)")
     ap.add_argument("--scratch-mib", type=int, default=0, help="override the inversion scratch cap (default 1 GiB: one chunk)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--halo", default="auto", choices=["auto", "peer", "exchange"],
+                    help="N > 1: read the neighbour's halo in place through a mapped peer pointer (default when available) "
+                         "or exchange it with NCCL send/recv")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -71,6 +71,15 @@ int pfb_analysis_execute_batched(pfb_analysis_plan* plan, const void* in_dev, vo
 int pfb_analysis_execute_segment(pfb_analysis_plan* plan, const void* in_dev, long long n_local,
                                  long long sample0, void* out_dev, int npol, long long k_first,
                                  long long nblk, int first_call, void* stream);
+/* The same, with the stream held in TWO buffers: samples [0, n_own) in in_dev and the following n_next samples in
+ * next_dev - in a time-sharded run the neighbour GPU's input buffer, mapped into this process (CUDA IPC /
+ * torch symmetric memory) and read over NVLink by the analysis kernel's own TMA copies.  This is the halo exchange of
+ * SURVEY 8(e) (the tail carry of FilterBank.m:85-88,119-126) without an exchange step: nothing is copied, no
+ * collective is called.  SKA-Low fast path only (PFB_ERR_UNSUPPORTED otherwise: exchange the halo instead);
+ * the caller guarantees the neighbour's samples are in place (one barrier after loading, not one per call). */
+int pfb_analysis_execute_segment_peer(pfb_analysis_plan* plan, const void* in_dev, long long n_own,
+                                      const void* next_dev, long long n_next, long long sample0, void* out_dev,
+                                      int npol, long long k_first, long long nblk, int first_call, void* stream);
 
 /* ---- inversion: replaces out = polyphase_synthesis(in, spans_nyquist, input_fft_length,
  *      os_factor, deripple, sample_offset, input_overlap, temporal_taper, spectral_taper,

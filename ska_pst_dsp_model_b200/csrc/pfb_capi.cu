@@ -441,6 +441,17 @@ template <typename T> static int analysis_launch(pfb_analysis_plan* p, AnalysisA
       if (rc) return rc;
     }
   }
+  if (a.in2) {
+    // peer-halo form: only the fast kernel reads two buffers; the generic kernel may serve head blocks whose
+    // windows lie inside the own buffer, nothing else
+    if (k_hi <= k_lo || k_hi < a.nblocks)
+      return fail(PFB_ERR_UNSUPPORTED, "peer-halo analysis needs the SKA-Low fast path over all blocks of the segment");
+    if (k_lo > 0 && a.start0 + (k_lo - 1) * (long long)a.S + (long long)a.P * a.N > a.n_own)
+      return fail(PFB_ERR_UNSUPPORTED, "peer-halo analysis: head blocks reach into the peer buffer");
+    AnalysisArgs h = a;
+    h.in2 = nullptr; h.n_dat = a.n_own;
+    return analysis_launch_generic<T>(h, 0, k_lo, st);
+  }
   if (k_hi <= k_lo) {
     bool done = false;
     int rc = analysis_launch_slide<T>(p, a, st, &done);
@@ -455,7 +466,7 @@ template <typename T> static int analysis_launch(pfb_analysis_plan* p, AnalysisA
 
 static int analysis_run(pfb_analysis_plan* p, const void* in, long long n_local, long long sample0, void* out,
                         int npol, long long k_first, long long nblk, long long kout0, long long kout_mod,
-                        int first_call, void* stream) {
+                        int first_call, void* stream, const void* in2 = nullptr, long long n_own = 0) {
   if (!p) return fail(PFB_ERR_ARG, "null plan");
   if (npol < 1 || npol > 2) return fail(PFB_ERR_ARG, "npol must be 1 or 2");
   if (nblk <= 0) return PFB_OK;                      // nothing to do (empty / too short input)
@@ -466,6 +477,7 @@ static int analysis_run(pfb_analysis_plan* p, const void* in, long long n_local,
   a.in = in; a.out = out; a.taps = p->d_taps; a.fft = p->fft;
   a.N = p->N; a.S = p->S; a.P = p->P; a.npol = npol;
   a.n_dat = n_local;
+  a.in2 = in2; a.n_own = in2 ? n_own : n_local;
   long long start_abs0 = 0, rot = 0;
   if (p->variant == PFB_VARIANT_PADDED) { start_abs0 = -(long long)p->fl; rot = 1; }
   if (p->variant == PFB_VARIANT_LOWCBF) { start_abs0 = first_call ? -1536 : 0; rot = first_call ? 1536 : 0; }
@@ -523,6 +535,19 @@ int pfb_analysis_execute_segment(pfb_analysis_plan* plan, const void* in_dev, lo
     return fail(PFB_ERR_UNSUPPORTED, "padded variant wraps its output circularly; segment form not defined");
   if (k_first < 0 || nblk < 0) return fail(PFB_ERR_ARG, "negative block range");
   return analysis_run(plan, in_dev, n_local, sample0, out_dev, npol, k_first, nblk, 0, 0, first_call, stream);
+}
+
+int pfb_analysis_execute_segment_peer(pfb_analysis_plan* plan, const void* in_dev, long long n_own, const void* next_dev,
+                                      long long n_next, long long sample0, void* out_dev, int npol, long long k_first,
+                                      long long nblk, int first_call, void* stream) {
+  if (!plan) return fail(PFB_ERR_ARG, "null plan");
+  if (plan->variant == PFB_VARIANT_PADDED)
+    return fail(PFB_ERR_UNSUPPORTED, "padded variant wraps its output circularly; segment form not defined");
+  if (k_first < 0 || nblk < 0 || n_own < 0 || n_next < 0) return fail(PFB_ERR_ARG, "negative size");
+  if (n_next > 0 && !next_dev) return fail(PFB_ERR_ARG, "null peer pointer");
+  if (n_next == 0) return analysis_run(plan, in_dev, n_own, sample0, out_dev, npol, k_first, nblk, 0, 0, first_call, stream);
+  return analysis_run(plan, in_dev, n_own + n_next, sample0, out_dev, npol, k_first, nblk, 0, 0, first_call, stream,
+                      next_dev, n_own);
 }
 
 // ---------------------------------------------------------------------------

@@ -36,6 +36,9 @@ struct AnalysisArgs {
   long long in_pitch, out_sk, out_sc, out_sp;
   // two-kernel form: arm sums already computed by pfb_fir_slide into ysrc[k][slot][pol]
   const void* ysrc;
+  // two-buffer form (fast SKA-Low kernel only): samples n_own.. of the stream live in in2 (a peer GPU's memory)
+  const void* in2;
+  long long n_own;
 };
 
 template <typename T>

@@ -115,8 +115,11 @@ struct AnaArgs {
   C* out;                // [k][chan][pol]
   const float* taps;     // [48][64]: taps[u][r] = scale * f[r + 64 u]
   const float2* tw;      // [3][64]:  exp(-2 pi i r o / 256), o = 1..3
+  const C* in2;          // continuation of the stream: samples n1.. live here (a neighbour GPU's buffer mapped over
+                         // NVLink in time-sharded runs; null: everything is in `in`)
+  long long n1;          // samples in `in` (== n_local when in2 is null)
   long long s0;          // window start of block 0 (>= 0, rotation-free: (phase0+s0) % 256 == 0)
-  long long n_local;     // samples resident in `in`
+  long long n_local;     // samples resident in `in` (+ `in2`)
   long long nblk;        // blocks to produce
   long long kout0;       // first output block slot
   int L;                 // blocks per CTA (multiple of 16)
@@ -160,8 +163,16 @@ __global__ void __launch_bounds__(64 * NPOL, NPOL == 2 ? 2 : 4) pfb_analysis_low
     uint64_t* bar = &full[i % kAnaStages];
     if (nbytes > 0) {
       mbar_expect_tx(bar, (uint32_t)nbytes);
-      tma_load_1d(ring + (size_t)(i % kAnaStages) * kTileSamples * NPOL, reinterpret_cast<const char*>(a.in) + b0,
-                  (uint32_t)nbytes, bar);
+      // the tile may straddle the end of `in`: the rest comes straight from the neighbour's memory (peer pointer,
+      // NVLink) - the halo of a time shard is never copied, the TMA engine reads it where it lives
+      const long long own_bytes = a.n1 * NPOL * (long long)sizeof(C);
+      long long na = own_bytes - b0;
+      if (na > nbytes) na = nbytes;
+      if (na < 0) na = 0;
+      char* dst = reinterpret_cast<char*>(ring + (size_t)(i % kAnaStages) * kTileSamples * NPOL);
+      if (na > 0) tma_load_1d(dst, reinterpret_cast<const char*>(a.in) + b0, (uint32_t)na, bar);
+      if (nbytes > na)
+        tma_load_1d(dst + na, reinterpret_cast<const char*>(a.in2) + (b0 + na - own_bytes), (uint32_t)(nbytes - na), bar);
     } else {
       mbar_arrive(bar);
     }
@@ -192,9 +203,12 @@ __global__ void __launch_bounds__(64 * NPOL, NPOL == 2 ? 2 : 4) pfb_analysis_low
   // window prologue: elements 0..44 of block kA's window straight from global
   C w[48];
   {
-    const C* p = a.in + (a.s0 + 192 * kA + r) * NPOL + pol;
+    const long long i0 = a.s0 + 192 * kA + r;
 #pragma unroll
-    for (int u = 0; u < 45; ++u) w[u] = ld_nc(p + (long long)u * 64 * NPOL);
+    for (int u = 0; u < 45; ++u) {
+      const long long idx = i0 + 64ll * u;
+      w[u] = ld_nc(idx < a.n1 ? a.in + idx * NPOL + pol : a.in2 + (idx - a.n1) * NPOL + pol);
+    }
   }
 
   for (int it = 0; it < niter; ++it) {
@@ -928,6 +942,7 @@ inline int low_analysis_launch<float>(const AnalysisArgs& g, const void* d_low, 
   // TMA source alignment: 16 bytes
   if (((uintptr_t)g.in + (uintptr_t)((s0 + 2880) * g.npol * 8)) % 16 != 0) return 0;
   if (g.npol == 1 && (((uintptr_t)g.in) % 16 != 0 || (s0 % 2) != 0)) return 0;
+  if (g.in2 && (((uintptr_t)g.in2) % 16 != 0 || ((uintptr_t)g.in) % 16 != 0 || (g.n_own * g.npol * 8) % 16 != 0)) return 0;
   const long long nblk = hi - lo;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
@@ -941,6 +956,8 @@ inline int low_analysis_launch<float>(const AnalysisArgs& g, const void* d_low, 
   const long long grid = (nblk + L - 1) / L;
   low::AnaArgs a;
   a.in = reinterpret_cast<const low::C*>(g.in);
+  a.in2 = reinterpret_cast<const low::C*>(g.in2);
+  a.n1 = g.in2 ? g.n_own : n_eff;
   a.out = reinterpret_cast<low::C*>(g.out);
   a.taps = h->taps; a.tw = h->tw;
   a.s0 = s0; a.n_local = n_eff; a.nblk = nblk; a.kout0 = g.kout0 + lo; a.L = (int)L;

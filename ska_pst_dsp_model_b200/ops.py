@@ -117,6 +117,20 @@ class AnalysisPlan:
         return out
 
 
+    def segment_peer(self, x_own, next_ptr, n_next, sample0, k_first, nblk, out=None, first_call=True):
+        """``segment`` with the stream in two buffers: ``x_own`` and the ``n_next`` samples that follow it at device
+        address ``next_ptr`` (a peer GPU's buffer mapped into this process): the halo is read in place over NVLink."""
+        _check_tensor(x_own, self.dtype, self.device, 2)
+        n_own, npol = x_own.shape
+        if out is None:
+            out = torch.empty((nblk, self.nchan_out, npol), dtype=self.dtype, device=self.device)
+        with torch.cuda.device(self.device):
+            _l.check(_l.lib.pfb_analysis_execute_segment_peer(self._h, x_own.data_ptr(), n_own, ctypes.c_void_p(int(next_ptr)),
+                                                              int(n_next), int(sample0), out.data_ptr(), npol, int(k_first),
+                                                              int(nblk), int(first_call), _stream_ptr(self.device)))
+        return out
+
+
 class InversePlan:
     """Golden FFT-based PFB inversion on one GPU."""
 

@@ -109,11 +109,30 @@ def exchange_halo(local, shard: TimeShard, group=None):
         req.wait()
 
 
+def map_peer_buffers(numel_max, dtype, device, group=None):
+    """One symmetric buffer per rank (torch.distributed._symmetric_memory: the allocation of every rank is mapped
+    into every other rank's address space over NVLink).  Returns (local tensor, [device pointer of every rank's
+    buffer]).  Plumbing only - the data path is the analysis kernel reading the neighbour's pointer."""
+    import torch
+    import torch.distributed as dist
+    import torch.distributed._symmetric_memory as symm_mem
+    t = symm_mem.empty(numel_max, dtype=dtype, device=device)
+    hdl = symm_mem.rendezvous(t, group if group is not None else dist.group.WORLD)
+    return t, [int(p) for p in hdl.buffer_ptrs], hdl
+
+
 class ShardedRoundTrip:
-    """Analysis + inversion of this rank's time shard (one process per GPU)."""
+    """Analysis + inversion of this rank's time shard (one process per GPU).
+
+    ``halo="peer"`` (default when the process group is NCCL and the symmetric-memory mapping succeeds): the rank's
+    input buffer is a symmetric allocation, and the analysis kernel reads the ``halo_n`` samples it needs from rank+1
+    straight out of that rank's buffer through a mapped pointer - one analysis launch, no exchange step, no
+    collective.  ``halo="exchange"``: the neighbour send/recv of ``start_halo_exchange`` (gloo / CPU tests, and the
+    fallback when peer mapping is unavailable)."""
 
     def __init__(self, shard: TimeShard, nchan, os_factor, taps, input_fft_length, input_overlap,
-                 temporal_taper="tukey", deripple=True, npol=2, dtype=None, device=None):
+                 temporal_taper="tukey", deripple=True, npol=2, dtype=None, device=None, halo="auto", group=None,
+                 shards=None):
         import torch
         from . import ops
         self.torch = torch
@@ -123,12 +142,43 @@ class ShardedRoundTrip:
         self.inverse = ops.InversePlan(nchan, os_factor, input_fft_length, input_overlap, temporal_taper,
                                        deripple_taps=taps if deripple else None, dtype=dtype, device=device)
         dev = self.analysis.device
-        self.local = torch.zeros((shard.own_n + shard.halo_n, npol), dtype=dtype, device=dev)
+        self.halo_mode = "exchange"
+        self.peer_error = None
+        self.next_ptr = 0
+        self._symm = None
+        if shard.world > 1 and halo in ("auto", "peer"):
+            try:
+                import torch.distributed as dist
+                # identical sizes on every rank: the longest shard (all ranks know every shard's size)
+                rows = max((sh.own_n + sh.halo_n) for sh in shards) if shards else None
+                if rows is None:
+                    t = torch.tensor([shard.own_n + shard.halo_n], dtype=torch.int64, device=dev)
+                    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+                    rows = int(t.item())
+                buf, ptrs, hdl = map_peer_buffers(rows * npol, dtype, dev, group)
+                self._symm = (buf, hdl)
+                self.local = buf.view(rows, npol)[: shard.own_n + shard.halo_n]
+                self.local.zero_()
+                if shard.rank + 1 < shard.world:
+                    self.next_ptr = ptrs[shard.rank + 1]
+                self.halo_mode = "peer"
+            except Exception as e:          # noqa: BLE001  (no P2P / symmetric memory: exchange instead)
+                if halo == "peer":
+                    raise
+                self.peer_error = repr(e)
+        if self.halo_mode != "peer":
+            self.local = torch.zeros((shard.own_n + shard.halo_n, npol), dtype=dtype, device=dev)
         self.chan = torch.empty((shard.fine_n, nchan, npol), dtype=dtype, device=dev)
         self.out = torch.empty((shard.out_n, npol), dtype=dtype, device=dev)
 
-    def load_owned(self, x_owned):
+    def load_owned(self, x_owned, group=None):
+        """Copy this rank's samples in; in peer mode every rank must have loaded before any rank runs (one barrier
+        here, none per step)."""
         self.local[: self.shard.own_n].copy_(x_owned)
+        if self.halo_mode == "peer":
+            import torch.distributed as dist
+            self.torch.cuda.synchronize()
+            dist.barrier(group=group)
 
     def step(self, group=None):
         self.run_analysis(group)
@@ -136,9 +186,14 @@ class ShardedRoundTrip:
         return self.out
 
     def run_analysis(self, group=None):
-        """Halo exchange overlapped with the analysis of the interior blocks (those whose FIR window
-        lies inside the owned samples), then the few tail blocks, then the inversion."""
+        """peer mode: one launch, the halo is read in place from rank+1.  exchange mode: halo exchange overlapped with
+        the analysis of the interior blocks (those whose FIR window lies inside the owned samples), then the tail
+        blocks."""
         s = self.shard
+        if self.halo_mode == "peer":
+            self.analysis.segment_peer(self.local[: s.own_n], self.next_ptr, s.halo_n, s.own0, s.fine0, s.fine_n,
+                                       out=self.chan)
+            return
         reqs = start_halo_exchange(self.torch.view_as_real(self.local), s, group)
         if not reqs:
             self.analysis.segment(self.local, s.own0, s.fine0, s.fine_n, out=self.chan)

@@ -117,3 +117,28 @@ def test_linearity_and_time_invariance_at_scale(pst_taps):
     # and the round trip reproduces the (delayed) input to the prototype filter's reconstruction error
     delay = 3072 // 2 + 36 * 256
     assert float((ya[:100000] - a[delay: delay + 100000]).abs().max() / a.abs().max()) < 2e-3
+
+
+@pytest.mark.parametrize("npol", [1, 2])
+def test_segment_peer_reads_second_buffer_in_place(pst_taps, npol):
+    """pfb_analysis_execute_segment_peer: the stream lives in two buffers (own samples + the neighbour's first
+    samples, here a second allocation on the same GPU standing in for a peer mapping); the result must be bit-identical
+    to the one-buffer segment call, wherever the cut falls inside a TMA tile or a CTA's window prologue."""
+    import torch
+    from ska_pst_dsp_model_b200 import ops
+    from ska_pst_dsp_model_b200.lib import PfbError
+    h = pst_taps / pst_taps.sum()
+    rng = np.random.default_rng(31)
+    nblk = 16 * 300 + 7
+    n = 3072 + 192 * (nblk - 1)
+    x = torch.from_numpy((rng.standard_normal((n, npol)) + 1j * rng.standard_normal((n, npol))).astype(np.complex64)).cuda()
+    ana = ops.AnalysisPlan(256, "4/3", h)
+    ref = ana.segment(x, 0, 0, nblk)
+    for cut in (n - 21312, n - 2880, n // 2 + 64, 192 * 16 * 150 + 2880 + 8):
+        own, nxt = x[:cut].clone(), x[cut:].clone()
+        got = ana.segment_peer(own, nxt.data_ptr(), nxt.shape[0], 0, 0, nblk)
+        assert torch.equal(got, ref), cut
+    # shapes without the two-buffer kernel refuse instead of silently copying
+    ana8 = ops.AnalysisPlan(8, "8/7", h)
+    with pytest.raises(PfbError):
+        ana8.segment_peer(x[:5000].clone(), x[5000:].data_ptr(), 1000, 0, 0, 100)
