@@ -485,6 +485,39 @@ def run_b200(args):
            "api": "streaming.HostRoundTrip.run(x_pinned, y_pinned): ops.AnalysisPlan.segment + ops.InversePlan over "
                   "the C ABI, H2D/kernels/D2H overlapped per time segment"}
 
+    # ---- the same with integer host buffers (NBIT 16 payloads in and out, DADARead.m:41-53): a separate key, the
+    #      headline e2e above stays the complex64 configuration BASELINE.json names
+    e2e_int16 = None
+    if not args.no_int16:
+        del hrt
+        hi = HostRoundTrip(shard.need_n, NCHAN, OS, taps, NFFT, OVERLAP, "tukey", True, NPOL, nseg=args.e2e_segments,
+                           device=dev, k_total=shard.fine_n, in_nbit=16, out_nbit=16, out_scale=1.0)
+        xi_host = torch.empty((shard.need_n, NPOL, 2), dtype=torch.int16).pin_memory()
+        xi_host.copy_(torch.view_as_real(x_host).mul(8192.0).round_().to(torch.int16))
+        yi_host = torch.empty((hi.n_out, NPOL, 2), dtype=torch.int16).pin_memory()
+        hi.run(xi_host, yi_host)
+        barrier()
+        s3, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s3.record()
+        for _ in range(Ke):
+            hi.run(xi_host, yi_host)
+        e3.record()
+        barrier()
+        ms_i = s3.elapsed_time(e3) / Ke
+        t = torch.tensor([ms_i], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_i = float(t.item())
+        # samples scaled by 8192 and rounded to int16; unity-gain round trip, so the int16 output / 8192 agrees with the
+        # float path to the two quantisation steps (~1e-4)
+        q = (torch.view_as_real(y_host[:65536]) - yi_host[:65536].to(torch.float32) / 8192.0).abs().max()
+        e2e_int16 = {"value": total_samples / (ms_i * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": ms_i,
+                     "h2d_bytes_per_step": sum(sg.need_n for sg in hi.segs) * NPOL * 4,
+                     "d2h_bytes_per_step": hi.n_out * NPOL * 4,
+                     "max_abs_diff_vs_float_path": float(q),
+                     "note": "int16 (re, im) host buffers both ways (NBIT 16 DADA payloads), cast on the device; "
+                             "half the PCIe bytes of the complex64 e2e"}
+        hrt = hi
     # quick in-bench sanity check of the result against the input (not the oracle):
     # the round trip reproduces the delayed input (unity gain, deripple on)
     y = rt.out[:4096, 0]
@@ -535,7 +568,7 @@ def run_b200(args):
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "config": workload_config(log2n, world, rt.halo_mode if world > 1 else None), "clocks": clocks, "e2e": e2e,
         "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline, "kernels": kernels,
-        "pipeline": pipeline, "sustained": sustained, "round_trip_max_err": rt_err,
+        "pipeline": pipeline, "sustained": sustained, "e2e_int16": e2e_int16, "round_trip_max_err": rt_err,
         "other_configs": other,
     }
     print(json.dumps(line), flush=True)
@@ -731,6 +764,7 @@ def main():
     ap.add_argument("--e2e-segments", type=int, default=8, help="base segment count of the host round trip (ramped head and tail add a few)")
     ap.add_argument("--scratch-mib", type=int, default=0, help="override the inversion scratch cap (default 1 GiB: one chunk)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-int16", action="store_true", help="skip the int16-payload end-to-end variant")
     ap.add_argument("--halo", default="auto", choices=["auto", "peer", "exchange"],
                     help="N > 1: read the neighbour's halo in place through a mapped peer pointer (default when available) "
                          "or exchange it with NCCL send/recv")

@@ -21,7 +21,12 @@ from .sharding import plan_time_shards
 
 class HostRoundTrip:
     def __init__(self, n_dat, nchan, os_factor, taps, input_fft_length, input_overlap, temporal_taper="tukey",
-                 deripple=True, npol=2, nseg=8, dtype=None, device=None, k_total=None, use_graph=True, nbuf=3, ramp=True):
+                 deripple=True, npol=2, nseg=8, dtype=None, device=None, k_total=None, use_graph=True, nbuf=3, ramp=True,
+                 in_nbit=None, out_nbit=None, out_scale=1.0):
+        """in_nbit / out_nbit = 8 or 16: the host buffers hold integer (re, im) pairs as in NBIT 8 / 16 DADA files
+        (DADARead.m:41-53; FilterBank.m:106-113 output rounding): ``x_host`` is int8/int16 ``[n_dat, npol, 2]``,
+        ``y_host`` int8/int16 ``[n_out, npol, 2]`` = round(out_scale * y) saturated.  The integers cross PCIe and are
+        cast on the device (pfb_unpack_payload / pfb_pack_payload): 2-4x fewer bytes on the link that bounds e2e."""
         import torch
         from . import ops
         self.torch = torch
@@ -52,6 +57,13 @@ class HostRoundTrip:
         self.din = [torch.empty((mx_in, npol), dtype=dtype, device=dev) for _ in range(self.nbuf)]
         self.dchan = [torch.empty((mx_fine, nchan, npol), dtype=dtype, device=dev) for _ in range(self.nbuf)]
         self.dout = [torch.empty((mx_out, npol), dtype=dtype, device=dev) for _ in range(self.nbuf)]
+        self.in_nbit, self.out_nbit, self.out_scale = in_nbit, out_nbit, float(out_scale)
+        idt = {8: torch.int8, 16: torch.int16}
+        if in_nbit or out_nbit:
+            if dtype != torch.complex64:
+                raise ValueError("integer payloads are implemented for the complex64 arithmetic type")
+        self.din_raw = [torch.empty((mx_in, npol, 2), dtype=idt[in_nbit], device=dev) for _ in range(self.nbuf)] if in_nbit else None
+        self.dout_raw = [torch.empty((mx_out, npol, 2), dtype=idt[out_nbit], device=dev) for _ in range(self.nbuf)] if out_nbit else None
         self.s_in, self.s_cmp, self.s_out = (torch.cuda.Stream(dev) for _ in range(3))
         self.use_graph = use_graph
         self._graphs = {}         # (x.data_ptr, y.data_ptr) -> captured step
@@ -111,6 +123,16 @@ class HostRoundTrip:
         g.replay()
         return y_host
 
+    def _convert(self, unpack, src, dst, nsamp, nbit):
+        import ctypes
+        from . import lib as _l
+        st = ctypes.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)
+        nval = 2 * nsamp * self.npol
+        if unpack:
+            _l.check(_l.lib.pfb_unpack_payload(src.data_ptr(), dst.data_ptr(), nval, nbit, _l.PFB_DTYPE_C64, st))
+        else:
+            _l.check(_l.lib.pfb_pack_payload(src.data_ptr(), dst.data_ptr(), nval, nbit, _l.PFB_DTYPE_C64, self.out_scale, st))
+
     def _enqueue(self, x_host, y_host):
         torch = self.torch
         cur = torch.cuda.current_stream(self.device)
@@ -123,7 +145,8 @@ class HostRoundTrip:
             with torch.cuda.stream(self.s_in):
                 if ev_cmp[slot] is not None:
                     self.s_in.wait_event(ev_cmp[slot])
-                self.din[slot][: sg.need_n].copy_(x_host[sg.need0: sg.need0 + sg.need_n], non_blocking=True)
+                dst = self.din_raw[slot] if self.in_nbit else self.din[slot]
+                dst[: sg.need_n].copy_(x_host[sg.need0: sg.need0 + sg.need_n], non_blocking=True)
                 ev_in = torch.cuda.Event()
                 ev_in.record(self.s_in)
             with torch.cuda.stream(self.s_cmp):
@@ -131,13 +154,18 @@ class HostRoundTrip:
                 if ev_out[slot] is not None:
                     self.s_cmp.wait_event(ev_out[slot])
                 ch = self.dchan[slot][: sg.fine_n]
+                if self.in_nbit:
+                    self._convert(True, self.din_raw[slot], self.din[slot], sg.need_n, self.in_nbit)
                 self.analysis.segment(self.din[slot][: sg.need_n], sg.need0, sg.fine0, sg.fine_n, out=ch)
                 self.inverse(ch, out=self.dout[slot][: sg.out_n])
+                if self.out_nbit:
+                    self._convert(False, self.dout[slot], self.dout_raw[slot], sg.out_n, self.out_nbit)
                 ev_cmp[slot] = torch.cuda.Event()
                 ev_cmp[slot].record(self.s_cmp)
             with torch.cuda.stream(self.s_out):
                 self.s_out.wait_event(ev_cmp[slot])
-                y_host[sg.out0: sg.out0 + sg.out_n].copy_(self.dout[slot][: sg.out_n], non_blocking=True)
+                src = self.dout_raw[slot] if self.out_nbit else self.dout[slot]
+                y_host[sg.out0: sg.out0 + sg.out_n].copy_(src[: sg.out_n], non_blocking=True)
                 ev_out[slot] = torch.cuda.Event()
                 ev_out[slot].record(self.s_out)
         cur.wait_stream(self.s_out)

@@ -89,3 +89,28 @@ def test_streaming_operators_on_integer_files(tmp_path, pst_taps, nbit):
     s2 = stream_synthesize(syn, str(p2), output_dir=str(tmp_path), output_file_name="stream.syn.dump", blocks_per_piece=2)
     a, b = open(s1.file_path, "rb").read(), open(s2.file_path, "rb").read()
     assert len(a) == len(b) and a == b
+
+
+def test_host_round_trip_with_integer_buffers(pst_taps):
+    """streaming.HostRoundTrip fed int16 host samples and returning int16: identical to the float path on the same
+    values (the device cast is exact) and to Matlab-rounding the float result on the host."""
+    import torch
+    from ska_pst_dsp_model_b200.streaming import HostRoundTrip
+    h = pst_taps / pst_taps.sum()
+    rng = np.random.default_rng(3)
+    n, npol = 3072 + 192 * 3000, 2
+    xi = rng.integers(-3000, 3000, (n, npol, 2)).astype(np.int16)
+    xf = (xi[..., 0].astype(np.float32) + 1j * xi[..., 1].astype(np.float32)).astype(np.complex64)
+    f = HostRoundTrip(n, 256, "4/3", h, 256, 48, "tukey", True, npol, nseg=4)
+    yf = torch.empty((f.n_out, npol), dtype=torch.complex64).pin_memory()
+    f.run(torch.from_numpy(xf).pin_memory(), yf)
+    torch.cuda.synchronize()
+    g = HostRoundTrip(n, 256, "4/3", h, 256, 48, "tukey", True, npol, nseg=4, in_nbit=16, out_nbit=16, out_scale=4.0)
+    yi = torch.empty((g.n_out, npol, 2), dtype=torch.int16).pin_memory()
+    g.run(torch.from_numpy(xi).pin_memory(), yi)
+    g.run(torch.from_numpy(xi).pin_memory(), yi)          # second call replays the captured graph
+    torch.cuda.synchronize()
+    yr = yf.numpy()
+    want = np.stack([o.matlab_round(4.0 * yr.real.astype(np.float64)), o.matlab_round(4.0 * yr.imag.astype(np.float64))], -1)
+    # fp32 product 4*y is exact (power of two), so the device rounding sees the same numbers
+    assert np.array_equal(yi.numpy(), np.clip(want, -32768, 32767).astype(np.int16))
