@@ -235,17 +235,19 @@ __global__ void __launch_bounds__(64 * NPOL, NPOL == 2 ? 2 : 4) pfb_analysis_low
       }
       // polyphase arms: acc[a] = sum_m tap[a+4m] * window[a+4m]
       C acc[4];
+      // packed fp32x2 FMA: (sx, sy) += tap * (v.x, v.y) is ONE instruction with a scalar tap operand (SASS FFMA2
+      // Rd, Ra.F32, Rb.F32x2, Rc.F32x2), i.e. 5 register reads per 2 MACs instead of 6 - the FIR is bound by
+      // register-file bandwidth, not by the FMA pipe
 #pragma unroll
       for (int ar = 0; ar < 4; ++ar) {
-        float sx = 0.f, sy = 0.f;
+        float2 s2 = make_float2(0.f, 0.f);
 #pragma unroll
         for (int m = 0; m < 12; ++m) {
           const int u = ar + 4 * m;
           const C v = w[(3 * j + u) % 48];
-          sx = fmaf(tap[u], v.x, sx);
-          sy = fmaf(tap[u], v.y, sy);
+          s2 = __ffma2_rn(make_float2(tap[u], tap[u]), make_float2(v.x, v.y), s2);
         }
-        acc[ar] = mk<float>(sx, sy);
+        acc[ar] = mk<float>(s2.x, s2.y);
       }
       // phase rotation: arm ar feeds FFT slot r + 64*((ar + 3j) mod 4)  ->  z[i] = acc[(i + j) mod 4]
       C z[4];
