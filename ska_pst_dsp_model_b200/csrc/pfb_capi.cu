@@ -726,6 +726,20 @@ static int launch_resample(pfb_inverse_plan* p, const void* v, void* out, int np
     if (rc) return fail(PFB_ERR_CUDA, "pfb_resample_low launch: %s", cudaGetErrorString((cudaError_t)rc));
     if (done) { p->prof_end(tok, st); return check_launch("pfb_resample_low"); }
   }
+  if (std::is_same<T, float>::value && p->mid_fast && p->Nf == 512 && p->ov == 128 && p->nu == 8 && p->de == 7 && p->spans &&
+      npol == 2 && G == 1 && p->nchan % 8 == 0 && ((uintptr_t)v % 16 == 0) && ((uintptr_t)out % 16 == 0) &&
+      nblk * (long long)(p->nchan / 8) < 2147483647ll) {
+    // SKA-Mid inversion shape: register-resident 512 -> 448 resample (pfb_mid.cuh)
+    mid::MidResArgs m;
+    m.v = reinterpret_cast<const mid::C*>(v); m.out = reinterpret_cast<mid::C*>(out);
+    m.taper = reinterpret_cast<const float*>(p->d_taper); m.wt = reinterpret_cast<const mid::C*>(p->d_wt);
+    m.tw512 = reinterpret_cast<const float2*>(p->fft_fwd.tw); m.tw448 = reinterpret_cast<const float2*>(p->fft_bwd.tw);
+    m.nchan = p->nchan; m.nblk = (int)nblk;
+    int rc = mid::resample_mid_launch(m, st);
+    if (rc) return fail(PFB_ERR_CUDA, "pfb_resample_mid launch: %s", cudaGetErrorString((cudaError_t)rc));
+    p->prof_end(tok, st);
+    return check_launch("pfb_resample_mid");
+  }
   ResampleArgs a;
   memset(&a, 0, sizeof(a));
   a.v = v; a.out = out; a.fwd = p->fft_fwd; a.bwd = p->fft_bwd; a.taper = p->d_taper; a.wt = p->d_wt;

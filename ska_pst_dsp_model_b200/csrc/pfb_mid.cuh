@@ -140,6 +140,130 @@ inline int rowfft4096_launch(const RowFftArgs& a, cudaStream_t st) {
 }
 
 // ---------------------------------------------------------------------------
+// K3 for the SKA-Mid inversion shape (polyphase_synthesis.m:163-316 at config "mid": Nf = 512, overlap 128, OS 8/7):
+// per column (t1, pol): taper -> 512-point FFT -> keep the 448 centre bins x W[t1][r] -> 448-point inverse FFT ->
+// keep the middle 224 outputs.  Same scheme as pfb_resample_low: 16 lanes per transform, lanes of a warp = 16
+// different columns (one 128-byte row segment per load / store), in-register butterflies with compile-time twiddles,
+// two exchanges through shared memory per column-block:
+//   512 = 32 x 16: lane q holds tau = q + 16 i (32 points) -> radix-32 -> x W512^(q o) -> exchange ->
+//                  lane l runs the radix-16 transforms of o = l and l + 16: bins b = o + 32 o2;
+//   kept bins are o2 in {0..6} U {9..15} for EVERY o, and their inverse-transform index is i' = o + 32 k, k = 0..13,
+//   so the 14-point inverse DFTs over k need no exchange (448 = 14 x 32);
+//   x W448^(o m) -> exchange -> lane m < 14 runs one radix-32 inverse: y[m + 14 j], kept j in [8, 24).
+// One CTA = 16 columns (8 t1 x 2 pol) x one overlap-save block; weights come straight from the 14.7 MB table
+// (L2-resident, every CTA of a column group re-reads the same 28 KB).
+constexpr int kMidCols = 16;
+constexpr int kMidStrideA = 32 * 17 + 1;     // [o (32)][q (16)] padded: odd pitch per column
+constexpr int kMidStrideB = 14 * 33 + 1;     // [m (14)][o (32)]
+
+struct MidResArgs {
+  const C* v;           // [tau][nchan][2]
+  C* out;               // [T2][nchan][2]
+  const float* taper;   // [512]
+  const C* wt;          // [nchan][448] in FN order
+  const float2* tw512;  // [512] exp(-2 pi i k/512)
+  const float2* tw448;  // [448] exp(-2 pi i k/448) (conjugated on load: the inverse transform)
+  int nchan, nblk;
+};
+
+constexpr size_t mid_res_smem_bytes() {
+  return (size_t)kMidCols * kMidStrideA * sizeof(C) + (512 + 448) * sizeof(C) + 512 * sizeof(float);
+}
+
+__global__ void __launch_bounds__(16 * kMidCols, 2) pfb_resample_mid(const MidResArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  C* ex = reinterpret_cast<C*>(smem_raw);              // [COLS][kMidStrideA], reused for the second exchange
+  C* t1s = ex + kMidCols * kMidStrideA;                // [32 o][16 q]  exp(-2 pi i q o / 512)
+  C* t2s = t1s + 512;                                  // [14 m][32 o]  exp(+2 pi i o m / 448)
+  float* stp = reinterpret_cast<float*>(t2s + 448);
+  const int tid = threadIdx.x;
+  const int c = tid % kMidCols, q = tid / kMidCols;    // column (t1 pair, pol), lane-in-transform
+  const int groups = a.nchan / (kMidCols / 2);
+  const int g = blockIdx.x % groups;
+  const long long n = blockIdx.x / groups;
+  const int t1_0 = g * (kMidCols / 2);
+  const long long rowlen = (long long)a.nchan * 2;
+
+  for (int i = tid; i < 512; i += 16 * kMidCols) {
+    stp[i] = a.taper[i];
+    const float2 w = __ldg(a.tw512 + (((i >> 4) * (i & 15)) & 511));
+    t1s[i] = mk<float>(w.x, w.y);
+  }
+  for (int i = tid; i < 448; i += 16 * kMidCols) {
+    const float2 w = __ldg(a.tw448 + (((i >> 5) * (i & 31)) % 448));
+    t2s[i] = mk<float>(w.x, -w.y);
+  }
+  __syncthreads();
+
+  const C* vcol = a.v + (long long)t1_0 * 2 + c + (n * 256 + q) * rowlen;
+  C* e = ex + c * kMidStrideA;
+  C x[32];
+  // phase 1: lane q holds tau = q + 16 i
+#pragma unroll
+  for (int i = 0; i < 32; ++i) x[i] = low::ld_nc(vcol + (long long)i * 16 * rowlen) * stp[q + 16 * i];
+  fft_reg<4, 8, -1>(x);
+#pragma unroll
+  for (int o = 0; o < 32; ++o) {
+    C u = x[slot<4, 8>(o)];
+    if (o) u = u * t1s[o * 16 + q];
+    e[o * 17 + q] = u;
+  }
+  __syncthreads();
+  // phase 2: lane l: o = l and l + 16; radix-16 over q -> bins b = o + 32 o2; keep o2 in {0..6} U {9..15}
+  C z[28];
+  const C* wrow = a.wt + (size_t)(t1_0 + (c >> 1)) * 448;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int o = q + 16 * h;
+    C y[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) y[i] = e[o * 17 + i];
+    fft_reg<4, 4, -1>(y);
+#pragma unroll
+    for (int k = 0; k < 14; ++k) {
+      const int o2 = k < 7 ? k : k + 2;
+      const int b = o + 32 * o2;                           // FFT bin
+      const int rr = b < 224 ? b + 224 : b - 288;          // FN-order index of that bin (fftshift + discard)
+      z[14 * h + k] = y[slot<4, 4>(o2)] * low::ld_nc(wrow + rr);
+    }
+  }
+  __syncthreads();                                         // all lanes done reading exchange A
+  // z[14 h + k] sits at inverse index i' = o + 32 k: 14-point inverse DFT over k, twiddle, second exchange
+  C* eb = ex + c * kMidStrideA;                            // [m][o] pitch 33
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int o = q + 16 * h;
+    fft_reg<2, 7, +1>(z + 14 * h);
+#pragma unroll
+    for (int m = 0; m < 14; ++m) {
+      C u = z[14 * h + slot<2, 7>(m)];
+      if (m) u = u * t2s[m * 32 + o];
+      eb[m * 33 + o] = u;
+    }
+  }
+  __syncthreads();
+  if (q < 14) {
+    // phase 3: lane m = q: y[m + 14 j] = sum_o eb[m][o] exp(+2 pi i o j / 32); keep j in [8, 24)
+    const int m = q;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) x[i] = eb[m * 33 + i];
+    fft_reg<4, 8, +1>(x);
+    C* p = a.out + (long long)t1_0 * 2 + c + (n * 224 - 112 + m) * rowlen;
+#pragma unroll
+    for (int j = 8; j < 24; ++j) p[(long long)14 * j * rowlen] = x[slot<4, 8>(j)];
+  }
+}
+
+inline int resample_mid_launch(const MidResArgs& a, cudaStream_t st) {
+  cudaError_t e = cudaFuncSetAttribute(pfb_resample_mid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mid_res_smem_bytes());
+  if (e != cudaSuccess) return (int)e;
+  const long long grid = (long long)a.nblk * (a.nchan / (kMidCols / 2));
+  if (grid > 2147483647ll) return (int)cudaErrorInvalidValue;
+  pfb_resample_mid<<<(unsigned)grid, 16 * kMidCols, mid_res_smem_bytes(), st>>>(a);
+  return (int)cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
 // Long power-of-two-times-24 spectra of dual-pol series (the 2 * block_size = 98 304 = 24 x 4096 point transforms of
 // the purity report, python/verify/purity.py:150,236-263, DomainPerformance.m:58-100): four-step FFT,
 //   X[k1 + 24 k2] = sum_n2 W4096^(n2 k2) * [ W_N^(n2 k1) * sum_n1 x[4096 n1 + n2] W24^(n1 k1) ],
