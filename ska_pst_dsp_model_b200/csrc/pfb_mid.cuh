@@ -163,7 +163,7 @@ struct MidResArgs {
   const C* wt;          // [nchan][448] in FN order
   const float2* tw512;  // [512] exp(-2 pi i k/512)
   const float2* tw448;  // [448] exp(-2 pi i k/448) (conjugated on load: the inverse transform)
-  int nchan, nblk;
+  int nchan, nblk, nsplit;
 };
 
 constexpr size_t mid_res_smem_bytes() {
@@ -179,8 +179,9 @@ __global__ void __launch_bounds__(16 * kMidCols, 2) pfb_resample_mid(const MidRe
   const int tid = threadIdx.x;
   const int c = tid % kMidCols, q = tid / kMidCols;    // column (t1 pair, pol), lane-in-transform
   const int groups = a.nchan / (kMidCols / 2);
-  const int g = blockIdx.x % groups;
-  const long long n = blockIdx.x / groups;
+  const int g = blockIdx.x % groups, sp = blockIdx.x / groups;
+  const int per = (a.nblk + a.nsplit - 1) / a.nsplit;
+  const int n_begin = sp * per, n_end = min(a.nblk, n_begin + per);
   const int t1_0 = g * (kMidCols / 2);
   const long long rowlen = (long long)a.nchan * 2;
 
@@ -195,8 +196,11 @@ __global__ void __launch_bounds__(16 * kMidCols, 2) pfb_resample_mid(const MidRe
   }
   __syncthreads();
 
-  const C* vcol = a.v + (long long)t1_0 * 2 + c + (n * 256 + q) * rowlen;
   C* e = ex + c * kMidStrideA;
+  // a CTA walks a run of consecutive blocks: the 256 rows two blocks share are read again a few microseconds later
+  // and come from L2 (the register file has no room for a 16-element carry next to the 32-point butterflies)
+  for (long long n = n_begin; n < n_end; ++n) {
+  const C* vcol = a.v + (long long)t1_0 * 2 + c + (n * 256 + q) * rowlen;
   C x[32];
   // phase 1: lane q holds tau = q + 16 i
 #pragma unroll
@@ -252,14 +256,26 @@ __global__ void __launch_bounds__(16 * kMidCols, 2) pfb_resample_mid(const MidRe
 #pragma unroll
     for (int j = 8; j < 24; ++j) p[(long long)14 * j * rowlen] = x[slot<4, 8>(j)];
   }
+  __syncthreads();                                         // exchange buffer free for the next block
+  }
 }
 
 inline int resample_mid_launch(const MidResArgs& a, cudaStream_t st) {
   cudaError_t e = cudaFuncSetAttribute(pfb_resample_mid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mid_res_smem_bytes());
   if (e != cudaSuccess) return (int)e;
-  const long long grid = (long long)a.nblk * (a.nchan / (kMidCols / 2));
+  // time splits: enough CTAs for ~4 resident waves (2 CTAs per SM), each walking a contiguous run of blocks
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const long long groups = a.nchan / (kMidCols / 2);
+  long long ns = (8ll * sms + groups - 1) / groups;
+  if (ns < 1) ns = 1;
+  if (ns > a.nblk) ns = a.nblk;
+  MidResArgs b = a;
+  b.nsplit = (int)ns;
+  const long long grid = ns * groups;
   if (grid > 2147483647ll) return (int)cudaErrorInvalidValue;
-  pfb_resample_mid<<<(unsigned)grid, 16 * kMidCols, mid_res_smem_bytes(), st>>>(a);
+  pfb_resample_mid<<<(unsigned)grid, 16 * kMidCols, mid_res_smem_bytes(), st>>>(b);
   return (int)cudaGetLastError();
 }
 

@@ -198,3 +198,39 @@ def test_purity_partial_reductions_merge():
     r = _merge_parts(m)[1, 2]
     o = np.argsort(p)
     assert np.allclose(r, [p.sum(), p.max(), p.sum(), p[o[-1]], p[o[-2]], o[-1], np.sqrt(p).sum(), p.size])
+
+
+def test_filter_designs_against_independent_least_squares(tmp_path):
+    """tools/design_filters.py: the firls designs (design_PFB_FIR_filter.m:24-48, design_PFB_FIR_filter_two_stage.m:42-78)
+    agree with an independent weighted least-squares solve (Gauss-Legendre quadrature of the error integral + numpy
+    lstsq on the cosine basis - no scipy.signal call), and the tool writes .mat / .txt / .npy with a SHA manifest that
+    read_fir_filter_coeff loads back."""
+    import json
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import design_filters as dfl
+    from ska_pst_dsp_model_b200.filters import design_pfb_fir_filter, read_fir_filter_coeff
+    for nchan, nu, de, tpc in [(8, 8, 7, 10), (64, 4, 3, 8)]:
+        h = design_pfb_fir_filter(nchan, nu, de, tpc)
+        osf = nu / de
+        ref = dfl.firls_reference(nchan * tpc + 1, [0, 1.0 / nchan, (2 * osf - 1) / nchan, 1.0], [1, 1, 0, 0], [1, 15])
+        assert h.size == nchan * tpc + 1 and np.abs(h - ref).max() <= 1e-9 * np.abs(ref).max()
+    # two-stage: the stage-1 design is the same least-squares problem at 32x the band edges (3137 taps); the long
+    # filter is its FFT-domain interpolation by 32: same passband / stopband behaviour on the 32x finer grid
+    from scipy.signal import firls, freqz
+    osf = 8.0 / 7.0
+    b1 = [0, 32.0 / 4096, 0.998 * 32 * (2 * osf - 1) / 4096, 1.0]
+    h0 = dfl.firls_reference(3137, b1, [1, 1, 0, 0], [1, 15], grid_per_tap=3)
+    assert np.abs(h0 - firls(3137, b1, [1, 1, 0, 0], weight=[1, 15])).max() < 1e-9 * np.abs(h0).max()
+    hm, meta = dfl.design("two_stage", 4096, "8/7")
+    assert hm.size == 100353 and abs(hm.sum() - 1.0) < 1e-3 and np.allclose(hm, hm[::-1], atol=1e-12)
+    w = np.linspace(0, np.pi / 64, 257)                       # two coarse channels' worth of the long filter's band
+    _, Hm = freqz(hm, 1, worN=w)
+    _, H0 = freqz(h0, 1, worN=32 * w)
+    assert np.abs(np.abs(Hm) - np.abs(H0)).max() < 2e-3
+    rec = dfl.write(hm, meta, str(tmp_path), "Prototype_FIR.2_stage.8-7.4096.100352")
+    man = json.load(open(tmp_path / "MANIFEST.json"))
+    assert man["Prototype_FIR.2_stage.8-7.4096.100352"]["sha256_coefficients"] == rec["sha256_coefficients"]
+    for ext in (".mat", ".txt", ".npy"):
+        back = read_fir_filter_coeff(str(tmp_path / ("Prototype_FIR.2_stage.8-7.4096.100352" + ext)))
+        assert np.array_equal(back, hm)
