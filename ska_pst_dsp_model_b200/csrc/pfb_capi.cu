@@ -16,6 +16,7 @@
 #include "pfb_mid.cuh"
 #include "pfb_payload.cuh"
 #include "pfb_purity.cuh"
+#include "pfb_small.cuh"
 
 using namespace pfb;
 
@@ -151,11 +152,13 @@ struct pfb_analysis_plan {
   const void* d_low_taps = nullptr; // fast Low kernel tap layout
   bool low_fast = false;
   bool mid_fast = true;             // shape-specialised SKA-Mid kernels allowed (PFB_NO_MID, read once at plan creation)
+  small8::Fir8Taps* fir8 = nullptr; // 8-channel 8/7 384-taps-per-arm shape (pfb_small.cuh): arm-major taps for the kernel parameters
   void* d_yscratch = nullptr;       // arm sums of the sliding-window FIR kernel
   size_t yscratch_cap = 0;
   DeviceTables tabs;
   ~pfb_analysis_plan() {
     if (d_yscratch) cudaFree(d_yscratch);
+    delete fir8;
   }
 };
 
@@ -257,6 +260,15 @@ int pfb_analysis_plan_create(pfb_analysis_plan** plan, int variant, int nchan, i
     rc = low_analysis_plan_init(p->N, p->nu, p->de, p->P, p->dtype, taps, p->ntaps, p->scale, &p->tabs.ptrs, &p->d_low_taps, &p->low_fast);
   if (rc > 0) rc = fail(PFB_ERR_CUDA, "fast-path table upload: %s", cudaGetErrorString((cudaError_t)rc));
   if (rc) { delete p; return rc; }
+  if (variant == PFB_VARIANT_BUNTON && dtype == PFB_DTYPE_C64 && nchan == 8 && os_nu == 8 && os_de == 7 &&
+      p->P == small8::kTaps && getenv("PFB_NO_SMALL8") == nullptr) {
+    p->fir8 = new small8::Fir8Taps();
+    for (int j = 0; j < 8; ++j)
+      for (int m = 0; m < small8::kTaps; ++m) {
+        const int n = j + 8 * m;
+        p->fir8->t[j][m] = n < ntaps ? (float)taps[n] : 0.f;
+      }
+  }
   *plan = p;
   return PFB_OK;
 }
@@ -430,8 +442,48 @@ static int analysis_launch_slide(pfb_analysis_plan* p, const AnalysisArgs& a, cu
   return PFB_OK;
 }
 
+// 8-channel, 384-taps-per-arm shape: register-sliding FIR with CTA-uniform taps, then the generic FFT stage
+template <typename T> static int analysis_launch_small8(pfb_analysis_plan* p, const AnalysisArgs& a, cudaStream_t st, bool* done) {
+  *done = false;
+  return PFB_OK;
+}
+template <> int analysis_launch_small8<float>(pfb_analysis_plan* p, const AnalysisArgs& a, cudaStream_t st, bool* done) {
+  *done = false;
+  if (!p->fir8 || a.npol != 1 || a.in2 || a.start0 < 0 || a.kout_mod != 0 || a.nblocks < 64 || ((uintptr_t)a.in % 8)) return PFB_OK;
+  const size_t need = (size_t)a.nblocks * 8 * sizeof(Cx<float>);
+  if (need > p->yscratch_cap) {
+    if (p->d_yscratch) CU(cudaFree(p->d_yscratch));
+    p->d_yscratch = nullptr; p->yscratch_cap = 0;
+    CU(cudaMalloc(&p->d_yscratch, need));
+    p->yscratch_cap = need;
+  }
+  small8::Fir8Args f;
+  f.in = reinterpret_cast<const small8::C*>(a.in);
+  f.y = reinterpret_cast<small8::C*>(p->d_yscratch);
+  f.n_dat = a.n_dat; f.nblocks = a.nblocks; f.start0 = a.start0;
+  f.rot = (int)((((a.phase0 + a.start0) % 8) + 8) % 8);
+  int rc = small8::fir8_launch(f, *p->fir8, st);
+  if (rc) return fail(PFB_ERR_CUDA, "pfb_fir8_slide launch: %s", cudaGetErrorString((cudaError_t)rc));
+  rc = check_launch("pfb_fir8_slide");
+  if (rc) return rc;
+  *done = true;
+  if (a.chan_first == 0 && a.nchan_out == 8 && ((uintptr_t)a.out % 16 == 0)) {
+    small8::pfb_fft8_store<<<(unsigned)((a.nblocks + 255) / 256), 256, 0, st>>>(
+        reinterpret_cast<const small8::C*>(p->d_yscratch), reinterpret_cast<small8::C*>(a.out), a.nblocks, a.kout0, (float)a.scale);
+    return check_launch("pfb_fft8_store");
+  }
+  AnalysisArgs b = a;
+  b.ysrc = p->d_yscratch;
+  return analysis_launch_generic<float>(b, 0, a.nblocks, st);
+}
+
 template <typename T> static int analysis_launch(pfb_analysis_plan* p, AnalysisArgs& a, cudaStream_t st) {
   if (a.nblocks <= 0) return PFB_OK;
+  {
+    bool done = false;
+    int rc = analysis_launch_small8<T>(p, a, st, &done);
+    if (rc || done) return rc;
+  }
   long long k_lo = 0, k_hi = 0;
   if (p->low_fast) {
     int rc = low_analysis_launch<T>(a, p->d_low_taps, st, &k_lo, &k_hi);

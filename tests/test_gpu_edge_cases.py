@@ -142,3 +142,27 @@ def test_segment_peer_reads_second_buffer_in_place(pst_taps, npol):
     ana8 = ops.AnalysisPlan(8, "8/7", h)
     with pytest.raises(PfbError):
         ana8.segment_peer(x[:5000].clone(), x[5000:].data_ptr(), 1000, 0, 0, 100)
+
+
+def test_cfg1_shape_fast_fir_whole_and_segments(pst_taps):
+    """8 channels, OS 8/7, PST taps (384 per arm): pfb_fir8_slide + FFT stage against the oracle on noise, for a whole
+    stream (last span partial) and for segments that start at arbitrary block offsets (every rotation 7k mod 8)."""
+    import torch
+    from ska_pst_dsp_model_b200 import ops
+    h = pst_taps / pst_taps.sum()
+    rng = np.random.default_rng(41)
+    nblk = 1280 * 3 + 411
+    n = 3072 + 7 * nblk + 5                      # nblocks = floor((n - fl) / S) (polyphase_analysis.m:62)
+    x = (rng.standard_normal((1, 1, n)) + 1j * rng.standard_normal((1, 1, n))).astype(np.complex64)
+    ref = o.polyphase_analysis(x.astype(np.complex128), h, 8, "8/7")
+    assert ref.shape == (1, 8, nblk)
+    ana = ops.AnalysisPlan(8, "8/7", h)
+    xd = torch.from_numpy(np.ascontiguousarray(x[0, 0, :, None])).cuda()
+    before = ops.launch_count()
+    got = ana(xd).cpu().numpy()[:, :, 0].T
+    assert ops.launch_count() - before == 2                       # FIR kernel + 8-point FFT stage
+    assert np.abs(got - ref[0]).max() / np.abs(ref).max() < 1e-5
+    for k_first, nb in [(1, 200), (13, 1500), (1283, 2000)]:
+        s0 = 7 * k_first - 3                                       # the segment buffer starts 3 samples before the window
+        seg = ana.segment(xd[s0:], s0, k_first, nb).cpu().numpy()[:, :, 0].T
+        assert np.abs(seg - ref[0][:, k_first: k_first + nb]).max() / np.abs(ref).max() < 1e-5, k_first
