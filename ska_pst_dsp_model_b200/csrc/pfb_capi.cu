@@ -176,6 +176,7 @@ struct pfb_inverse_plan {
   bool low_fast = false;
   bool mid_fast = true;              // PFB_NO_MID / PFB_NO_WS: debugging switches, read once at plan creation
   bool ws_fast = true;
+  bool taper_unity_mid = false;      // temporal taper == 1 on [ov, Nf - ov)
   long long scratch_bytes = 1024ll << 20;   // one chunk for streams up to ~2^25 samples/pol at the SKA-Low shape
   void* d_scratch = nullptr;
   size_t scratch_cap = 0;
@@ -628,6 +629,9 @@ static int inverse_build(pfb_inverse_plan* p, const double* taper, const double*
   const T* dtp;
   if ((rc = p->tabs.upload(tp, &dtp))) return rc;
   p->d_taper = dtp;
+  p->taper_unity_mid = true;
+  for (int i = p->ov; i < p->Nf - p->ov; ++i)
+    if (tp[(size_t)i] != (T)1) p->taper_unity_mid = false;
   // deripple weights in FN order (polyphase_synthesis.m:142-149, 244-250)
   const int pb = p->FNw / 2;
   std::vector<double> w(p->FNw, 1.0);
@@ -787,7 +791,7 @@ static int launch_resample(pfb_inverse_plan* p, const void* v, void* out, int np
     m.taper = reinterpret_cast<const float*>(p->d_taper); m.wt = reinterpret_cast<const mid::C*>(p->d_wt);
     m.tw512 = reinterpret_cast<const float2*>(p->fft_fwd.tw); m.tw448 = reinterpret_cast<const float2*>(p->fft_bwd.tw);
     m.nchan = p->nchan; m.nblk = (int)nblk;
-    int rc = mid::resample_mid_launch(m, st);
+    int rc = mid::resample_mid_launch(m, p->taper_unity_mid, st);
     if (rc) return fail(PFB_ERR_CUDA, "pfb_resample_mid launch: %s", cudaGetErrorString((cudaError_t)rc));
     p->prof_end(tok, st);
     return check_launch("pfb_resample_mid");

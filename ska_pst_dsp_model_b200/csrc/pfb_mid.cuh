@@ -170,6 +170,9 @@ constexpr size_t mid_res_smem_bytes() {
   return (size_t)kMidCols * kMidStrideA * sizeof(C) + (512 + 448) * sizeof(C) + 512 * sizeof(float);
 }
 
+// UNITY_MID: the temporal taper is exactly 1 on [ov, Nf - ov) (Tukey, top-hat interior, no window): only the 16 edge
+// samples of a lane are scaled.
+template <bool UNITY_MID>
 __global__ void __launch_bounds__(16 * kMidCols, 2) pfb_resample_mid(const MidResArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   C* ex = reinterpret_cast<C*>(smem_raw);              // [COLS][kMidStrideA], reused for the second exchange
@@ -204,7 +207,10 @@ __global__ void __launch_bounds__(16 * kMidCols, 2) pfb_resample_mid(const MidRe
   C x[32];
   // phase 1: lane q holds tau = q + 16 i
 #pragma unroll
-  for (int i = 0; i < 32; ++i) x[i] = low::ld_nc(vcol + (long long)i * 16 * rowlen) * stp[q + 16 * i];
+  for (int i = 0; i < 32; ++i) {
+    x[i] = low::ld_nc(vcol + (long long)i * 16 * rowlen);
+    if (!UNITY_MID || i < 8 || i >= 24) x[i] = x[i] * stp[q + 16 * i];       // ov = 128 = 8 * 16
+  }
   fft_reg<4, 8, -1>(x);
 #pragma unroll
   for (int o = 0; o < 32; ++o) {
@@ -215,7 +221,7 @@ __global__ void __launch_bounds__(16 * kMidCols, 2) pfb_resample_mid(const MidRe
   __syncthreads();
   // phase 2: lane l: o = l and l + 16; radix-16 over q -> bins b = o + 32 o2; keep o2 in {0..6} U {9..15}
   C z[28];
-  const C* wrow = a.wt + (size_t)(t1_0 + (c >> 1)) * 448;
+  const C* wrow = a.wt + (size_t)(t1_0 + (c >> 1)) * 448;      // (staging the 28 KB in shared memory was measured: 5 % slower)
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
     const int o = q + 16 * h;
@@ -260,8 +266,9 @@ __global__ void __launch_bounds__(16 * kMidCols, 2) pfb_resample_mid(const MidRe
   }
 }
 
-inline int resample_mid_launch(const MidResArgs& a, cudaStream_t st) {
-  cudaError_t e = cudaFuncSetAttribute(pfb_resample_mid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mid_res_smem_bytes());
+inline int resample_mid_launch(const MidResArgs& a, bool unity_mid, cudaStream_t st) {
+  auto kern = unity_mid ? pfb_resample_mid<true> : pfb_resample_mid<false>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mid_res_smem_bytes());
   if (e != cudaSuccess) return (int)e;
   // time splits: enough CTAs for ~4 resident waves (2 CTAs per SM), each walking a contiguous run of blocks
   int dev = 0, sms = 148;
@@ -275,7 +282,7 @@ inline int resample_mid_launch(const MidResArgs& a, cudaStream_t st) {
   b.nsplit = (int)ns;
   const long long grid = ns * groups;
   if (grid > 2147483647ll) return (int)cudaErrorInvalidValue;
-  pfb_resample_mid<<<(unsigned)grid, 16 * kMidCols, mid_res_smem_bytes(), st>>>(b);
+  kern<<<(unsigned)grid, 16 * kMidCols, mid_res_smem_bytes(), st>>>(b);
   return (int)cudaGetLastError();
 }
 

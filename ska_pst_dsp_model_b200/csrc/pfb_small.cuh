@@ -48,14 +48,31 @@ __global__ void __launch_bounds__(kThreads, 2)
   const int j = blockIdx.y;
   const long long k0 = (long long)blockIdx.x * kSpanBlocks;
   const long long s0 = a.start0 + 7 * k0;
-  for (int t = threadIdx.x; t < kTileSamples; t += kThreads) {
-    const long long s = s0 + t;
-    C v = mk<float>(0.f, 0.f);
-    if (s < a.n_dat) {
-      const float2 r = __ldg(reinterpret_cast<const float2*>(a.in + s));
-      v = mk<float>(r.x, r.y);
+  if ((s0 & 1) == 0 && ((uintptr_t)a.in % 16) == 0) {
+    // two samples per 16-byte load, 8 independent loads in flight per thread (the tile is 96 KB: a serial load loop
+    // would cost more than the FIR itself)
+    const float4* src = reinterpret_cast<const float4*>(a.in + s0);
+    float4* dst = reinterpret_cast<float4*>(tile);
+    const long long avail = a.n_dat - s0;                  // samples left in the stream from the tile start
+#pragma unroll 8
+    for (int t = threadIdx.x; t < kTileSamples / 2; t += kThreads) {
+      float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (2ll * t + 1 < avail) r = __ldg(src + t);
+      dst[t] = r;
     }
-    tile[t] = v;
+    if ((avail & 1) && avail > 0 && avail <= kTileSamples && threadIdx.x == 0) {   // odd stream end inside the tile
+      const float2 q = __ldg(reinterpret_cast<const float2*>(a.in + s0 + avail - 1));
+      __syncwarp(0x1);
+      tile[avail - 1] = mk<float>(q.x, q.y);
+    }
+  } else {
+#pragma unroll 8
+    for (int t = threadIdx.x; t < kTileSamples; t += kThreads) {
+      const long long s = s0 + t;
+      float2 r = make_float2(0.f, 0.f);
+      if (s < a.n_dat) r = __ldg(reinterpret_cast<const float2*>(a.in + s));
+      tile[t] = mk<float>(r.x, r.y);
+    }
   }
   __syncthreads();
   const int p = threadIdx.x & 7, c = threadIdx.x >> 3;
