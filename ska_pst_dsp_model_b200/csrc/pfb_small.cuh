@@ -6,16 +6,19 @@
 //  * gcd(7, 8) = 1, but blocks k and k + 8 read the same sub-stream u[n] = x[7 p + j + 8 n] (p = k mod 8, arm j)
 //    shifted by 7 elements, so a thread that owns (arm j, phase p) slides along u: output i needs u[7 i + m], m < 384.
 //  * a CTA owns ONE arm (blockIdx.y), so its 384 taps are CTA-uniform: they come from the kernel-parameter constant bank
-//    into uniform registers and cost no vector-register read - the packed FMA (acc.xy += tap * u.xy, FFMA2) then reads
-//    two register pairs only and issues at the full fp32 rate (a three-operand FFMA holds the issue port two cycles,
-//    DESIGN.md section 5);
+//    (one indexed LDC per tap) and stay in the operand-reuse cache for the 5 packed FMAs that use them
+//    (SASS: FFMA2 Rd, Rtap.reuse.F32, Rw.F32x2, Racc.F32x2): two fresh register pairs per FFMA2.  Measured: the kernel
+//    runs at ~0.3 of the nominal fp32 FMA roof - a packed FMA with two fresh 64-bit operands issues every ~4 cycles
+//    (register-file bandwidth), so ~0.5 is the ceiling of this instruction mix;
 //  * every thread computes R = 5 outputs i0..i0+4 at once: their sample indices at tap m are u[7 i0 + m + {0,7,..,28}],
 //    a 29-element window that slides by ONE element per tap, held in a 32-slot circular register file with static
 //    indices (the tap loop is unrolled 32-fold, 12 iterations): one shared-memory load per 5 packed FMAs.
 //    R is odd so that the two chunks sharing a shared-memory wavefront sit 8 (mod 16) eight-byte units apart, next to
 //    the eight phases' 7 p (mod 16): conflict-free;
 //  * the arm sums go to a [k][slot] scratch with the oversampling rotation already applied (slot = (7 k + j) mod 8);
-//    pfb_fft8_store runs the 8-point FFTs (one per thread, in registers) and the scaled store.
+//    pfb_fft8_store runs the 8-point FFTs (one per thread, in registers) and the scaled store.  (A fused form - 8 warps
+//    = 8 arms per CTA, FFT stage from shared memory in the same kernel - was measured: 22.5 us against 18.4 us for the
+//    two kernels, the serial FFT tail of every CTA costs more than the second launch.)
 #pragma once
 #include "pfb_generic.cuh"
 

@@ -257,3 +257,45 @@ class TwoStageInverseFilterBank:
         if self.buffered_samples > 0:
             self.input_buffer = x[input_idat:].clone()
         return out.contiguous()
+
+
+class TwoStageGraph:
+    """One block of the two-stage chain as a single captured launch graph: stage-1 analysis ->
+    stage-2 analysis of all coarse channels (one batched launch) -> critical chomp -> stage-2 inversion of all coarse
+    channels (one batched launch, optional ``combine``), i.e. ``TwoStageInverseFilterBank.execute(
+    TwoStageFilterBank.execute(x))`` (TwoStageFilterBank.m:58-116, TwoStageInverseFilterBank.m:75-157) for the FIRST
+    block of a stream of fixed length ``n_dat`` (no carried tails inside the graph: a streaming caller feeds blocks
+    that already contain their history, like ``file_streaming``).  Buffers are static; ``run(x)`` copies the block in,
+    replays the graph and returns views of the static outputs."""
+
+    def __init__(self, cfg1: dict, cfg2: dict, icfg: dict, n_dat: int, critical=False, combine=1, invert=True):
+        torch = _torch()
+        self.fb = TwoStageFilterBank(cfg1, cfg2, critical=critical)
+        nch2 = self.fb.stage2.n_chan
+        os2 = self.fb.stage2.os_factor
+        self.inv = TwoStageInverseFilterBank(icfg, nch2=(nch2 * os2.de // os2.nu if critical else nch2),
+                                             stage2_nchan=nch2, combine=combine) if invert else None
+        self.x = torch.zeros((int(n_dat), 1), dtype=torch.complex64, device="cuda")
+        self._fresh()
+        self.fine = self.fb.execute(self.x)                      # warm-up: plans built, scratch sized, shapes fixed
+        self.y = self.inv.execute(self.fine) if self.inv is not None else None
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        cap = torch.cuda.Stream()
+        cap.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.graph(self.graph, stream=cap, capture_error_mode="thread_local"):
+            self._fresh()
+            self.fine = self.fb.execute(self.x)
+            self.y = self.inv.execute(self.fine) if self.inv is not None else None
+        torch.cuda.current_stream().wait_stream(cap)
+
+    def _fresh(self):
+        for f in (self.fb.stage1, self.fb.stage2):
+            f.buffered_samples, f.input_buffer, f._first_call = 0, None, True
+        if self.inv is not None:
+            self.inv.buffered_samples, self.inv.input_buffer = 0, None
+
+    def run(self, x):
+        self.x.copy_(x.reshape(self.x.shape))
+        self.graph.replay()
+        return self.fine, self.y

@@ -183,3 +183,27 @@ def test_two_stage_low_scale_frequency_comb(critical, invert, combine, pst_taps)
     # TestFrequencyComb's bin prediction in this set-up (polyphase_synthesis.m:253-255 stitches the
     # fft-shifted channels without the half-channel rotation); parity with the oracle is what is pinned.
     assert passed == (_comb_check(ref, freqs, "4/3", two_stage=True, invert=True, critical=critical) == 0)
+
+
+@pytest.mark.parametrize("critical,combine", [(False, 1), (True, 1), (True, 2)])
+def test_two_stage_chain_as_one_graph(critical, combine):
+    """TwoStageGraph: stage 1 -> batched stage 2 -> chomp -> batched stage-2 inversion captured as ONE CUDA graph;
+    replays on new data equal the class-by-class chain (and through it the oracle classes)."""
+    import torch
+    from ska_pst_dsp_model_b200.filterbank import TwoStageFilterBank, TwoStageGraph, TwoStageInverseFilterBank
+    rng = np.random.default_rng(8)
+    h8 = o.design_pfb_fir_filter(8, "4/3", 6)
+    cfg = dict(filt_coeff=h8, n_chan=8, os_factor="4/3")
+    icfg = dict(filt_coeff=h8, n_fft=24, overlap=4, os_factor="4/3")
+    n = 6000
+    g = TwoStageGraph(cfg, cfg, icfg, n, critical=critical, combine=combine)
+    nch2 = 6 if critical else 8
+    for seed in (1, 2):
+        x = cn(np.random.default_rng(seed), (1, 1, n))
+        fine, y = g.run(dev(x))
+        torch.cuda.synchronize()
+        f_ref = TwoStageFilterBank(cfg, critical=critical).execute(dev(x))
+        y_ref = TwoStageInverseFilterBank(icfg, nch2=nch2, stage2_nchan=8, combine=combine).execute(f_ref)
+        assert torch.equal(fine, f_ref) and torch.equal(y, y_ref)
+        r = o.TwoStageFilterBank(cfg, critical=critical).execute(x.astype(np.complex128))
+        assert nerr(host(fine), r) < 1e-5

@@ -61,37 +61,36 @@ if "--skip-mid" not in sys.argv:
                    "analysis_Msamples_s": 2 * n / ms_a / 1e3, "round_trip_Msamples_s": 2 * n / (ms_a + ms_i) / 1e3,
                    "nblocks": int(chm.shape[0]), "kernels": "pfb_fir_phases + pfb_rowfft4096 (analysis), pfb_rowfft4096 + generic resample (inversion)"}
     del xm, chm, ana, inv
-# two-stage (Low scale as in test_sgcht options 4-8): 256 coarse x 256 fine channels, 4/3 both
-# stages, stage 2 and its inversion as ONE batched launch over all coarse channels
-from ska_pst_dsp_model_b200.filterbank import TwoStageFilterBank, TwoStageInverseFilterBank
+# two-stage: the whole chain of one block as ONE captured CUDA graph
+# (filterbank.TwoStageGraph): stage 1 -> batched stage 2 over all coarse channels -> chomp -> batched stage-2 inversion.
+from ska_pst_dsp_model_b200.filterbank import TwoStageGraph
 n2 = 1 << 23
 x2 = torch.view_as_complex(torch.randn((n2, 1, 2), device="cuda"))
 cfg = dict(filt_coeff=h, n_chan=256, os_factor="4/3")
-_tsf = TwoStageFilterBank(cfg, critical=False)
-
-
-def tsf():
-    for fb in (_tsf.stage1, _tsf.stage2):                     # same input every call: no carried tail
-        fb.buffered_samples, fb.input_buffer = 0, None
-    return _tsf.execute(x2)
-
-
-fine = tsf()
 icfg = dict(filt_coeff=h, n_fft=128, overlap=16, os_factor="4/3", temporal_taper="tukey")
-_tsi = TwoStageInverseFilterBank(icfg, nch2=256, stage2_nchan=256, combine=1)
-
-
-def tsi():
-    _tsi.buffered_samples, _tsi.input_buffer = 0, None       # same input every call: no carried tail
-    return _tsi.execute(fine)
-ms_f, ms_b = timeit(tsf, 3), timeit(tsi, 3)
-res["two_stage_low"] = {"shape": "2^23 x 1 pol -> 256 coarse x 256 fine channels (4/3 x 4/3, PST taps), inversion of stage 2 "
-                                 "(Nf=128, ov=16) for all coarse channels in one batched launch",
-                        "analysis_ms": ms_f, "stage2_inversion_ms": ms_b, "fine_shape": list(fine.shape),
-                        "analysis_Msamples_s": n2 / ms_f / 1e3,
-                        "kernels": "stage 1: pfb_analysis_low<1>; stage 2: generic batched analysis; inversion: "
-                                   "generic channel IDFT + pfb_resample_low (batched columns)"}
-del x2, fine
+for critical, combine in ((False, 1), (True, 16)):
+    tg = TwoStageGraph(cfg, cfg, icfg, n2, critical=critical, combine=combine)
+    ms = timeit(lambda: tg.run(x2), 5)
+    res[f"two_stage_low_graph_critical{int(critical)}_combine{combine}"] = {
+        "shape": "2^23 x 1 pol -> 256 coarse x 256 fine channels (4/3 x 4/3, PST taps) -> stage-2 inversion (Nf=128, ov=16); "
+                 "one CUDA graph replay per block (incl. the 64 MiB input copy)",
+        "ms_per_block": ms, "Msamples_s": n2 / ms / 1e3, "fine_shape": list(tg.fine.shape), "out_shape": list(tg.y.shape)}
+    del tg
+del x2
+if "--skip-mid" not in sys.argv and "--two-stage-mid" in sys.argv:
+    # SKA-Mid two-stage analysis at scale (TwoStageFilterBank.m:58-116 with the mid config for both stages): 2^29 samples
+    # -> 4096 coarse channels x 149 796 samples -> 41 stage-2 blocks of 4096 fine channels each.  The stage-2 INVERSION
+    # needs >= 512 stage-2 blocks per coarse channel, i.e. 6.6e9 input samples (53 GB): not run (nor can sgcht.m's
+    # 2 x 64 Mi-sample run produce it, sgcht.m:481-484).
+    hm2 = design_pfb_fir_filter_two_stage(4096, 8, 7)
+    cfgm = dict(filt_coeff=hm2, n_chan=4096, os_factor="8/7", analysis_function="polyphase_analysis_padded")
+    nm = 1 << 29
+    xm2 = torch.view_as_complex(torch.randn((nm, 1, 2), device="cuda"))
+    tgm = TwoStageGraph(cfgm, cfgm, None, nm, critical=True, invert=False)
+    ms = timeit(lambda: tgm.run(xm2), 2)
+    res["two_stage_mid_graph_analysis"] = {"shape": "2^29 x 1 pol -> 4096 coarse x 3584 kept fine channels (critical), one graph",
+                                           "ms_per_block": ms, "Msamples_s": nm / ms / 1e3, "fine_shape": list(tgm.fine.shape)}
+    del xm2, tgm
 # file -> file through the streaming operators: 2^24 x 2 pol complex64 DADA file (256 MiB) channelized
 # to 341 MiB and inverted to 255 MiB, pieces read into pinned memory / written by I/O threads
 import tempfile
