@@ -153,6 +153,7 @@ struct pfb_analysis_plan {
   bool low_fast = false;
   bool mid_fast = true;             // shape-specialised SKA-Mid kernels allowed (PFB_NO_MID, read once at plan creation)
   small8::Fir8Taps* fir8 = nullptr; // 8-channel 8/7 384-taps-per-arm shape (pfb_small.cuh): arm-major taps for the kernel parameters
+  const float4* d_fir8_btab = nullptr;   // tensor-core form of the same FIR (PFB_FIR8_MMA=1 at plan creation): B fragments
   void* d_yscratch = nullptr;       // arm sums of the sliding-window FIR kernel
   size_t yscratch_cap = 0;
   DeviceTables tabs;
@@ -269,6 +270,33 @@ int pfb_analysis_plan_create(pfb_analysis_plan** plan, int variant, int nchan, i
         const int n = j + 8 * m;
         p->fir8->t[j][m] = n < ntaps ? (float)taps[n] : 0.f;
       }
+    if (getenv("PFB_FIR8_MMA") != nullptr) {
+      // B fragments of mma.m16n8k8 (col-major 8 x 8): lane holds B[k = tig][n = gid] and B[tig + 4][gid];
+      // B[t][a] = f_j[t - 7 a]; hi = TF32(x) (round to nearest, ties away: keep 10 mantissa bits), lo = TF32(x - hi)
+      auto tf32 = [](float x) {
+        uint32_t u;
+        memcpy(&u, &x, 4);
+        u = (u + 0x1000u) & 0xffffe000u;
+        float r;
+        memcpy(&r, &u, 4);
+        return r;
+      };
+      std::vector<float4> bt((size_t)8 * small8::kMmaKSteps * 32);
+      for (int j = 0; j < 8; ++j)
+        for (int ks = 0; ks < small8::kMmaKSteps; ++ks)
+          for (int lane = 0; lane < 32; ++lane) {
+            const int gid = lane >> 2, tig = lane & 3;
+            float v[2];
+            for (int h = 0; h < 2; ++h) {
+              const int m = 8 * ks + tig + 4 * h - 7 * gid;
+              v[h] = (m >= 0 && m < small8::kTaps) ? p->fir8->t[j][m] : 0.f;
+            }
+            const float h0 = tf32(v[0]), h1 = tf32(v[1]);
+            bt[((size_t)j * small8::kMmaKSteps + ks) * 32 + lane] = make_float4(h0, h1, tf32(v[0] - h0), tf32(v[1] - h1));
+          }
+      int rc2 = p->tabs.upload(bt, &p->d_fir8_btab);
+      if (rc2) { delete p; return rc2; }
+    }
   }
   *plan = p;
   return PFB_OK;
@@ -463,9 +491,18 @@ template <> int analysis_launch_small8<float>(pfb_analysis_plan* p, const Analys
   f.y = reinterpret_cast<small8::C*>(p->d_yscratch);
   f.n_dat = a.n_dat; f.nblocks = a.nblocks; f.start0 = a.start0;
   f.rot = (int)((((a.phase0 + a.start0) % 8) + 8) % 8);
-  int rc = small8::fir8_launch(f, *p->fir8, st);
-  if (rc) return fail(PFB_ERR_CUDA, "pfb_fir8_slide launch: %s", cudaGetErrorString((cudaError_t)rc));
-  rc = check_launch("pfb_fir8_slide");
+  int rc;
+  if (p->d_fir8_btab) {
+    small8::Fir8MmaArgs g;
+    g.in = f.in; g.y = f.y; g.btab = p->d_fir8_btab; g.n_dat = f.n_dat; g.nblocks = f.nblocks; g.start0 = f.start0; g.rot = f.rot;
+    rc = small8::fir8_mma_launch(g, st);
+    if (rc) return fail(PFB_ERR_CUDA, "pfb_fir8_mma launch: %s", cudaGetErrorString((cudaError_t)rc));
+    rc = check_launch("pfb_fir8_mma");
+  } else {
+    rc = small8::fir8_launch(f, *p->fir8, st);
+    if (rc) return fail(PFB_ERR_CUDA, "pfb_fir8_slide launch: %s", cudaGetErrorString((cudaError_t)rc));
+    rc = check_launch("pfb_fir8_slide");
+  }
   if (rc) return rc;
   *done = true;
   if (a.chan_first == 0 && a.nchan_out == 8 && ((uintptr_t)a.out % 16 == 0)) {

@@ -166,3 +166,24 @@ def test_cfg1_shape_fast_fir_whole_and_segments(pst_taps):
         s0 = 7 * k_first - 3                                       # the segment buffer starts 3 samples before the window
         seg = ana.segment(xd[s0:], s0, k_first, nb).cpu().numpy()[:, :, 0].T
         assert np.abs(seg - ref[0][:, k_first: k_first + nb]).max() / np.abs(ref).max() < 1e-5, k_first
+
+
+def test_cfg1_tensor_core_form_matches_oracle(pst_taps, monkeypatch):
+    """The tensor-core form of the 8-channel FIR (mma.sync TF32 with the 3xTF32 split, selected by PFB_FIR8_MMA at plan
+    creation; an experiment, the CUDA-core kernel is the default) holds the fp32 tolerance against the oracle."""
+    import torch
+    from ska_pst_dsp_model_b200 import ops
+    h = pst_taps / pst_taps.sum()
+    rng = np.random.default_rng(43)
+    nblk = 1024 * 3 + 77
+    n = 3072 + 7 * nblk + 3
+    x = (rng.standard_normal((1, 1, n)) + 1j * rng.standard_normal((1, 1, n))).astype(np.complex64)
+    ref = o.polyphase_analysis(x.astype(np.complex128), h, 8, "8/7")
+    xd = torch.from_numpy(np.ascontiguousarray(x[0, 0, :, None])).cuda()
+    base = ops.AnalysisPlan(8, "8/7", h)(xd).cpu().numpy()[:, :, 0].T
+    monkeypatch.setenv("PFB_FIR8_MMA", "1")
+    mma = ops.AnalysisPlan(8, "8/7", h)(xd).cpu().numpy()[:, :, 0].T
+    e_base = np.abs(base - ref[0]).max() / np.abs(ref).max()
+    e_mma = np.abs(mma - ref[0]).max() / np.abs(ref).max()
+    print(f"cfg1 FIR error vs fp64 oracle: CUDA cores {e_base:.2e}, tensor cores (3xTF32) {e_mma:.2e}")
+    assert e_base < 1e-5 and e_mma < 1e-5 and not np.array_equal(base, mma)
