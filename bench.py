@@ -448,6 +448,40 @@ def run_b200(args):
                      "note": "frac = dominant kernel's own compulsory bytes / its CUDA-event time / measured copy peak; "
                              "pipeline_frac = SURVEY 8(d) round-trip bytes (16(1+OS) B/sample) / step time / the same peak"})
 
+    # ---- fused analysis -> inversion (own key, never `value`): for in-process pipelines that do not need the channelized
+    #      data as a FILE, the analysis kernel writes the inversion's intermediate itself and the channel-IDFT kernel is
+    #      not run (ops.round_trip).  The drop-in synthesize() reads channelized files and cannot use this.
+    fused = None
+    if world == 1 and not args.no_fused:
+        try:
+            fused = {}
+            x_all = rt.local[: shard.own_n]                      # the whole 2^24-sample stream of this GPU
+            nb_all = rt.analysis.nblocks(x_all.shape[0])
+            assert rt.inverse.out_len(nb_all) == rt.out.shape[0]
+            ch_all = torch.empty((nb_all, NCHAN, NPOL), dtype=torch.complex64, device=dev)
+            for nm, want in (("with_channelized_output", True), ("inversion_only_output", False)):
+                ch_buf = ch_all if want else None
+                ops.round_trip(rt.analysis, rt.inverse, x_all, chan=ch_buf, out=rt.out)
+                torch.cuda.synchronize()
+                s4, e4 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s4.record()
+                for _ in range(K):
+                    ops.round_trip(rt.analysis, rt.inverse, x_all, chan=ch_buf, out=rt.out)
+                e4.record()
+                torch.cuda.synchronize()
+                ms_f = s4.elapsed_time(e4) / K
+                fused[nm] = {"ms_per_step": ms_f, "value": samples_rank / (ms_f * 1e-3) / 1e6, "unit": UNIT,
+                             "vs_three_kernel_step": ms_step / ms_f}
+            fused["note"] = ("analysis writes N x its rotated arm sums = the inversion's channel-IDFT intermediate; 2 kernels "
+                             "instead of 3; in-process pipelines only (purity sweep, host round trip), not the file drop-in")
+            del ch_all
+            # leave rt.out / rt.chan as the three-kernel step produced them for the checks below
+            rt.run_analysis()
+            rt.inverse(rt.chan, out=rt.out)
+            torch.cuda.synchronize()
+        except Exception as e:          # noqa: BLE001
+            fused = {"error": repr(e)}
+
     # ---- e2e: pinned host buffers through the public streaming operator ------
     # (H2D of the rank's samples incl. halo, kernels, D2H of the inverted series, overlapped
     #  over time segments on three streams; the host buffer already holds every halo)
@@ -568,7 +602,7 @@ def run_b200(args):
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "config": workload_config(log2n, world, rt.halo_mode if world > 1 else None), "clocks": clocks, "e2e": e2e,
         "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline, "kernels": kernels,
-        "pipeline": pipeline, "sustained": sustained, "e2e_int16": e2e_int16, "round_trip_max_err": rt_err,
+        "pipeline": pipeline, "sustained": sustained, "fused_round_trip": fused, "e2e_int16": e2e_int16, "round_trip_max_err": rt_err,
         "other_configs": other,
     }
     print(json.dumps(line), flush=True)
@@ -788,6 +822,7 @@ def main():
     ap.add_argument("--scratch-mib", type=int, default=0, help="override the inversion scratch cap (default 1 GiB: one chunk)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-int16", action="store_true", help="skip the int16-payload end-to-end variant")
+    ap.add_argument("--no-fused", action="store_true", help="skip the fused analysis->inversion side measurement")
     ap.add_argument("--halo", default="auto", choices=["auto", "peer", "exchange"],
                     help="N > 1: read the neighbour's halo in place through a mapped peer pointer (default when available) "
                          "or exchange it with NCCL send/recv")

@@ -106,6 +106,20 @@ int pfb_inverse_execute_batched(pfb_inverse_plan* plan, const void* in_dev, void
 /* spectral (frequency-domain) taper of polyphase_synthesis.m:282 / InverseFilterBank.frequency_taper:
  * n = nchan*FN_width doubles multiplying the stitched spectrum (NULL clears it).  With a taper set
  * the inversion runs the literal-order chain (per-channel FFT -> weights -> channel IDFT -> bin IFFT). */
+/* ---- fused analysis -> inversion in one process (python/data_gen/pipeline.py:62-84 followed by synthesize, or the
+ *      generate -> channelize -> synthesize pass of verify/purity.py:165-207, WITHOUT a channelized file in between).
+ *      The inverse DFT across channels of a channelized block equals N x the rotated polyphase arm sums the analysis
+ *      kernel holds before its FFT, so the analysis writes the inversion's intermediate directly and the channel-IDFT
+ *      kernel is not run.  chan_dev may be NULL (the channelized block is not wanted: the analysis then skips its FFT
+ *      stage as well).  SKA-Low dual-pol complex64 fast path only: PFB_ERR_UNSUPPORTED otherwise (call
+ *      pfb_analysis_execute + pfb_inverse_execute instead).  NOT a replacement for the file-based drop-in:
+ *      synthesize() reads channelized files and uses pfb_inverse_execute. */
+int pfb_roundtrip_execute(pfb_analysis_plan* aplan, pfb_inverse_plan* iplan, const void* in_dev, void* chan_dev,
+                          void* out_dev, int npol, long long n_dat, void* stream);
+/* the same for nvec independent vectors of vec_samples samples laid back to back (vec_samples a multiple of step and
+ * nchan): in [nvec * vec_samples][npol] -> out [nvec][n_blocks * output_keep][npol] */
+int pfb_roundtrip_execute_vectors(pfb_analysis_plan* aplan, pfb_inverse_plan* iplan, const void* in_dev, void* out_dev,
+                                  int npol, int nvec, long long vec_samples, void* stream);
 /* nvec independent channelized series stored back to back, row pitch vec_rows (>= n_dat) fine samples each:
  * in [nvec][vec_rows][nchan][npol] -> out [nvec][n_blocks*output_keep][npol].  Replaces the per-vector synthesize
  * call of the purity sweep (python/verify/purity.py:175-177, matlab/current_performance.m:261-299); one launch per

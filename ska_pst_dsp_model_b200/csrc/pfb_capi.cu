@@ -1137,6 +1137,72 @@ int pfb_inverse_execute_vectors(pfb_inverse_plan* p, const void* in_dev, void* o
                                    : inverse_run_vectors<double>(p, in_dev, out_dev, npol, nvec, vec_rows, n_dat, st);
 }
 
+// ---------------------------------------------------------------------------
+// Fused analysis -> inversion (one process, no channelized file in between): sum_c out[c] W^(-c t1) = N * acc_rot[t1],
+// i.e. the rotated arm sums of the analysis ARE the inversion's channel-IDFT intermediate.  The analysis kernel writes
+// them into the inverse plan's grouped scratch (and, optionally, the channelized block as usual) and the resample
+// kernel follows; the channel IDFT kernel is not run.  SKA-Low dual-pol fast path only.
+static int roundtrip_run(pfb_analysis_plan* ap, pfb_inverse_plan* ip, const void* in, void* chan, void* out, int npol,
+                         long long n_total, int nvec, long long vec_samples, cudaStream_t st) {
+  if (!ap->low_fast || ap->variant != PFB_VARIANT_BUNTON || ap->dtype != PFB_DTYPE_C64 || !ip->low_fast || !ip->ws_fast ||
+      ip->dtype != PFB_DTYPE_C64 || ip->spectral || npol != 2 || ip->nchan != ap->N || !low_ws_ok(ip->d_low, 2, 1, in, out) ||
+      ap->device != ip->device)
+    return fail(PFB_ERR_UNSUPPORTED, "fused round trip: SKA-Low dual-pol complex64 fast path only");
+  const long long nb_total = pfb_analysis_nblocks(ap, n_total, 1);
+  const long long nb_vec = nvec > 1 ? pfb_analysis_nblocks(ap, vec_samples, 1) : nb_total;
+  const long long nbi = pfb_inverse_nblocks(ip, nb_vec);
+  if (nb_total <= 0 || nbi <= 0) return PFB_OK;
+  if (nvec > 1 && (vec_samples % ap->S || vec_samples % ap->N))
+    return fail(PFB_ERR_ARG, "fused round trip of a vector batch: the vector length must be a multiple of step and nchan");
+  const long long vec_rows = nvec > 1 ? vec_samples / ap->S : nb_total;
+  const long long rows_cap = nvec > 1 ? (long long)nvec * vec_rows : nb_total;
+  const size_t need = (size_t)rows_cap * 256 * 16;
+  if ((long long)need > ip->scratch_bytes)
+    return fail(PFB_ERR_UNSUPPORTED, "fused round trip: %zu bytes of scratch exceed the plan's cap (pfb_inverse_set_scratch_bytes)", need);
+  if (need > ip->scratch_cap) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(st, &cs);
+    if (cs != cudaStreamCaptureStatusNone) return fail(PFB_ERR_ARG, "fused round trip: scratch must grow during stream capture; run once first");
+    if (ip->d_scratch) CU(cudaFree(ip->d_scratch));
+    ip->d_scratch = nullptr; ip->scratch_cap = 0;
+    CU(cudaMalloc(&ip->d_scratch, need));
+    ip->scratch_cap = need;
+  }
+  AnalysisArgs a;
+  memset(&a, 0, sizeof(a));
+  a.in = in; a.out = chan; a.taps = ap->d_taps; a.fft = ap->fft;
+  a.N = ap->N; a.S = ap->S; a.P = ap->P; a.npol = npol; a.n_dat = n_total; a.n_own = n_total;
+  a.start0 = 0; a.phase0 = 0; a.nblocks = nb_total; a.kout0 = 0; a.kout_mod = 0;
+  a.chan_first = ap->chan_first; a.nchan_out = ap->nchan_out; a.scale = ap->scale;
+  a.emit_mode = chan ? 1 : 2; a.vout = ip->d_scratch; a.v_rows_cap = rows_cap;
+  long long k_lo = 0, k_hi = 0;
+  int rc = low_analysis_launch<float>(a, ap->d_low_taps, st, &k_lo, &k_hi);
+  if (rc) return fail(PFB_ERR_CUDA, "pfb_analysis_low (fused) launch: %s", cudaGetErrorString((cudaError_t)rc));
+  if (k_lo != 0 || k_hi != nb_total)
+    return fail(PFB_ERR_UNSUPPORTED, "fused round trip: the fast analysis kernel does not cover the whole stream (alignment / length)");
+  rc = check_launch("pfb_analysis_low");
+  if (rc) return rc;
+  return launch_resample<float>(ip, ip->d_scratch, out, npol, (long long)nvec * nbi, st, 1, true, rows_cap,
+                                nvec > 1 ? vec_rows : 0, nvec > 1 ? nbi : 0);
+}
+
+int pfb_roundtrip_execute(pfb_analysis_plan* ap, pfb_inverse_plan* ip, const void* in_dev, void* chan_dev, void* out_dev,
+                          int npol, long long n_dat, void* stream) {
+  if (!ap || !ip) return fail(PFB_ERR_ARG, "null plan");
+  if (!in_dev || !out_dev || n_dat < 0) return fail(PFB_ERR_ARG, "pfb_roundtrip_execute: bad argument");
+  CU(cudaSetDevice(ap->device));
+  return roundtrip_run(ap, ip, in_dev, chan_dev, out_dev, npol, n_dat, 1, n_dat, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int pfb_roundtrip_execute_vectors(pfb_analysis_plan* ap, pfb_inverse_plan* ip, const void* in_dev, void* out_dev, int npol,
+                                  int nvec, long long vec_samples, void* stream) {
+  if (!ap || !ip) return fail(PFB_ERR_ARG, "null plan");
+  if (!in_dev || !out_dev || nvec < 1 || vec_samples < 1) return fail(PFB_ERR_ARG, "pfb_roundtrip_execute_vectors: bad argument");
+  CU(cudaSetDevice(ap->device));
+  return roundtrip_run(ap, ip, in_dev, nullptr, out_dev, npol, (long long)nvec * vec_samples, nvec, vec_samples,
+                       reinterpret_cast<cudaStream_t>(stream));
+}
+
 int pfb_inverse_execute_stage(pfb_inverse_plan* p, int stage, const void* in_dev, void* out_dev, int npol,
                               long long n_dat, void* stream) {
   if (!p || !in_dev || !out_dev) return fail(PFB_ERR_ARG, "null pointer");

@@ -39,6 +39,10 @@ struct AnalysisArgs {
   // two-buffer form (fast SKA-Low kernel only): samples n_own.. of the stream live in in2 (a peer GPU's memory)
   const void* in2;
   long long n_own;
+  // fused round trip (fast SKA-Low kernel only): 1 = also write the inversion intermediate v, 2 = v only
+  int emit_mode;
+  void* vout;
+  long long v_rows_cap;
 };
 
 template <typename T>

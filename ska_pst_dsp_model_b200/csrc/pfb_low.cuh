@@ -124,6 +124,11 @@ struct AnaArgs {
   long long kout0;       // first output block slot
   int L;                 // blocks per CTA (multiple of 16)
   int chan_first, nchan_out;
+  // fused round trip (EMIT > 0): the rotated arm sums ARE the channel-inverse-DFT of the channelized block
+  // (sum_c out[c] W^(-c t1) = N * acc_rot[t1]), so the analysis writes them straight into the resample kernel's grouped
+  // scratch and the channel IDFT kernel is not run at all
+  char* v;               // grouped scratch (grouped_unit), rows = output block slots
+  long long v_rows_cap;
 };
 
 constexpr int kAnaStages = 3;
@@ -135,9 +140,14 @@ template <int NPOL> constexpr size_t ana_smem_bytes() {
   return (size_t)kAnaStages * kTileSamples * NPOL * sizeof(C) + (size_t)64 * NPOL * kExStride * sizeof(C) + 64;
 }
 
+__device__ __forceinline__ long long grouped_unit(long long rows_cap, long long row, int t1);
+
 // FULL: all 256 channels are written in natural order (Bunton); otherwise the runtime channel
 // window (chan_first, nchan_out) of the lowcbf variant applies.
-template <int NPOL, bool FULL>
+// EMIT: 0 = channelized output only; 1 = channelized output + the inversion's intermediate v (dual-pol, fused
+// analysis -> inversion in one process); 2 = v only (the channelized data is not wanted: the 64-point FFT stage and
+// its stores are compiled out).
+template <int NPOL, bool FULL, int EMIT = 0>
 __global__ void __launch_bounds__(64 * NPOL, NPOL == 2 ? 2 : 4) pfb_analysis_low(const AnaArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   C* ring = reinterpret_cast<C*>(smem_raw);                                  // [stage][768][NPOL]
@@ -253,6 +263,18 @@ __global__ void __launch_bounds__(64 * NPOL, NPOL == 2 ? 2 : 4) pfb_analysis_low
       C z[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) z[i] = acc[(i + j) & 3];
+      if (EMIT > 0) {
+        // v[row][t1 = r + 64 i][pol] = N * z[i]: 16 consecutive r of a warp fill two whole 128-byte group rows
+        const long long row = a.kout0 + kA + 16ll * it + j;
+        if (kA + 16ll * it + j < kend) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const long long u = grouped_unit(a.v_rows_cap, row, r + 64 * i);
+            *reinterpret_cast<C*>(a.v + u * 16 + pol * 8) = mk<float>(256.f * z[i].x, 256.f * z[i].y);
+          }
+        }
+      }
+      if (EMIT == 2) continue;
       Dft<4, -1, float>::run(z);
       z[1] = z[1] * tw[0];
       z[2] = z[2] * tw[1];
@@ -265,6 +287,7 @@ __global__ void __launch_bounds__(64 * NPOL, NPOL == 2 ? 2 : 4) pfb_analysis_low
       for (int o = 0; o < 4; ++o)
         ex[(size_t)((((j >> 1) * NPOL + pol) * 8 + (j & 1) * 4) + o) * kExStride + r] = z[o];
     }
+    if (EMIT == 2) continue;
     __syncthreads();
     {
       // one 64-point FFT per thread (task = block j, pol, o), two radix-8 passes over the
@@ -971,7 +994,13 @@ inline int low_analysis_launch<float>(const AnalysisArgs& g, const void* d_low, 
     if (e != cudaSuccess) return;
     kernel<<<(unsigned)grid, threads, smem, st>>>(a);
   };
-  if (g.npol == 2) {
+  a.v = reinterpret_cast<char*>(g.vout);
+  a.v_rows_cap = g.v_rows_cap;
+  if (g.emit_mode > 0) {
+    if (!(g.npol == 2 && full && g.vout)) return (int)cudaErrorInvalidValue;
+    if (g.emit_mode == 1) go(low::pfb_analysis_low<2, true, 1>, low::ana_smem_bytes<2>(), 128);
+    else go(low::pfb_analysis_low<2, true, 2>, low::ana_smem_bytes<2>(), 128);
+  } else if (g.npol == 2) {
     if (full) go(low::pfb_analysis_low<2, true>, low::ana_smem_bytes<2>(), 128);
     else go(low::pfb_analysis_low<2, false>, low::ana_smem_bytes<2>(), 128);
   } else {

@@ -22,7 +22,7 @@ EXPORTS = [
     "pfb_inverse_execute_stage", "pfb_inverse_set_profiling", "pfb_inverse_get_profile",
     "pfb_inverse_set_spectral_taper", "pfb_generate_test_vector", "pfb_purity_metrics",
     "pfb_analysis_execute_batched", "pfb_inverse_execute_batched", "pfb_generate_test_vector_strided",
-    "pfb_generate_test_vectors", "pfb_unpack_payload", "pfb_pack_payload", "pfb_inverse_reserve", "pfb_inverse_execute_vectors", "pfb_spectrum_vectors", "pfb_purity_metrics_pairs", "pfb_analysis_execute_segment_peer",
+    "pfb_generate_test_vectors", "pfb_unpack_payload", "pfb_pack_payload", "pfb_inverse_reserve", "pfb_inverse_execute_vectors", "pfb_spectrum_vectors", "pfb_purity_metrics_pairs", "pfb_analysis_execute_segment_peer", "pfb_roundtrip_execute", "pfb_roundtrip_execute_vectors",
 ]
 
 PFB_DTYPE_C64, PFB_DTYPE_C128 = 0, 1
@@ -54,6 +54,8 @@ def _load():
     lib.pfb_analysis_execute.argtypes = [c_vp, c_vp, c_vp, c_int, c_ll, c_int, c_vp]
     lib.pfb_analysis_execute_segment.argtypes = [c_vp, c_vp, c_ll, c_ll, c_vp, c_int, c_ll, c_ll, c_int, c_vp]
     lib.pfb_analysis_execute_segment_peer.argtypes = [c_vp, c_vp, c_ll, c_vp, c_ll, c_ll, c_vp, c_int, c_ll, c_ll, c_int, c_vp]
+    lib.pfb_roundtrip_execute.argtypes = [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_ll, c_vp]
+    lib.pfb_roundtrip_execute_vectors.argtypes = [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_ll, c_vp]
     lib.pfb_inverse_plan_create.argtypes = [ctypes.POINTER(c_vp), c_int, c_int, c_int, c_int, c_int, dp, dp, c_int,
                                             c_int, c_int, c_int, c_int]
     lib.pfb_inverse_plan_destroy.argtypes = [c_vp]

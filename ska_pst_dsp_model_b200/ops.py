@@ -254,3 +254,20 @@ class InversePlan:
 
 def launch_count():
     return int(_l.lib.pfb_launch_count())
+
+
+def round_trip(analysis: AnalysisPlan, inverse: InversePlan, x, chan=None, out=None, want_chan=False):
+    """Fused analysis -> inversion of a device-resident stream (``pfb_roundtrip_execute``): the analysis kernel writes the
+    inversion's channel-IDFT intermediate itself.  Returns (chan or None, y).  Raises PfbError for shapes outside the
+    SKA-Low dual-pol fast path (use the two plans separately there)."""
+    _check_tensor(x, analysis.dtype, analysis.device, 2)
+    n_dat, npol = x.shape
+    nb = analysis.nblocks(n_dat)
+    if want_chan and chan is None:
+        chan = torch.empty((nb, analysis.nchan_out, npol), dtype=analysis.dtype, device=analysis.device)
+    if out is None:
+        out = torch.empty((inverse.out_len(nb), npol), dtype=analysis.dtype, device=analysis.device)
+    with torch.cuda.device(analysis.device):
+        _l.check(_l.lib.pfb_roundtrip_execute(analysis._h, inverse._h, x.data_ptr(), chan.data_ptr() if chan is not None else None,
+                                              out.data_ptr(), npol, n_dat, _stream_ptr(analysis.device)))
+    return chan, out

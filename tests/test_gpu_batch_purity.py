@@ -32,13 +32,13 @@ def oracle_round_trip(x, h, taper):
     return o.polyphase_synthesis(ch, True, 256, "4/3", h, 1, 48, taper)[0, 0]
 
 
-@pytest.mark.parametrize("use_graph", [False, True])
-def test_batched_chunk_equals_per_vector_oracle(pst_taps, use_graph):
+@pytest.mark.parametrize("use_graph,fused", [(False, False), (True, True), (False, True)])
+def test_batched_chunk_equals_per_vector_oracle(pst_taps, use_graph, fused):
     from ska_pst_dsp_model_b200.batch import BatchPurity
     h = pst_taps / pst_taps.sum()
     taper = o.window_tukey(256, 48)
-    bp = BatchPurity("4/3", 256, 48, "tukey", True, 256, h, 3, vectors_per_batch=6, use_graph=use_graph)
-    assert bp.concat and bp.vec_rows == 768 and bp.nb_vec == 752 and bp.n_out == 4 * 30720
+    bp = BatchPurity("4/3", 256, 48, "tukey", True, 256, h, 3, vectors_per_batch=6, use_graph=use_graph, fused=fused)
+    assert bp.concat and bp.vec_rows == 768 and bp.nb_vec == 752 and bp.n_out == 4 * 30720 and bp.fused == fused
     n = bp.n_samples
     # --- impulses: 5 vectors (odd count: the spare slot repeats the last one), offsets incl. both ends
     offs = np.array([0, 12000, 40001, 70000, 140000])
@@ -120,3 +120,32 @@ def test_matlab_offset_grid(pst_taps):
         assert v in p
     rep = bp.temporal(p[:6])
     assert len(rep) == 6 and all(r["max_spurious_power"] < -60 for r in rep if 9216 + 1536 < r["arg"] < 100000)
+
+
+def test_fused_round_trip_matches_oracle_and_two_plan_form(pst_taps):
+    """ops.round_trip (pfb_roundtrip_execute): the analysis kernel writes the inversion's channel-IDFT intermediate itself
+    (N x the rotated arm sums) - with and without the channelized output - and the result equals the oracle and the
+    two-plan form to fp32 rounding."""
+    import torch
+    from ska_pst_dsp_model_b200 import ops
+    from ska_pst_dsp_model_b200.lib import PfbError
+    h = pst_taps / pst_taps.sum()
+    rng = np.random.default_rng(17)
+    n = 3072 + 192 * (16 * 70 + 5)
+    x = (rng.standard_normal((n, 2)) + 1j * rng.standard_normal((n, 2))).astype(np.complex64)
+    xd = torch.from_numpy(x).cuda()
+    ana = ops.AnalysisPlan(256, "4/3", h)
+    inv = ops.InversePlan(256, "4/3", 256, 48, "tukey", deripple_taps=h)
+    ch_ref = ana(xd)
+    y_two = inv(ch_ref)
+    ch, y1 = ops.round_trip(ana, inv, xd, want_chan=True)
+    _, y2 = ops.round_trip(ana, inv, xd)
+    assert torch.equal(ch, ch_ref)                                  # the channelized output is the same kernel code
+    assert torch.equal(y1, y2)
+    xo = np.ascontiguousarray(x.T[:, None, :]).astype(np.complex128)
+    y_ref = o.polyphase_synthesis(o.polyphase_analysis(xo, h, 256, "4/3"), True, 256, "4/3", h, 1, 48, o.window_tukey(256, 48))
+    got = y1.cpu().numpy().T[:, None, :]
+    assert got.shape == y_ref.shape and nerr(got, y_ref) < TOL
+    assert nerr(y_two.cpu().numpy(), y1.cpu().numpy()) < 2e-6
+    with pytest.raises(PfbError):                                    # other shapes: not fused
+        ops.round_trip(ops.AnalysisPlan(8, "8/7", h), ops.InversePlan(8, "8/7", 256, 48, "tukey"), xd[:, :1].contiguous())
