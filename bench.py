@@ -777,6 +777,22 @@ def measure_other_configs(dev, peak, cpu=True):
                                                     min(workers, 16))
     del xm, chm, ym, ana, inv
     torch.cuda.empty_cache()
+    # ---- fp64 mode of the bench workload (north star: <= 1e-6 in an fp64 mode): generic kernels, complex128 -----
+    n = 1 << 22
+    x64 = torch.view_as_complex(torch.randn((n, 2, 2), device=dev, dtype=torch.float64, generator=g))
+    ana = ops.AnalysisPlan(NCHAN, OS, h, dtype=torch.complex128, device=dev)
+    inv = ops.InversePlan(NCHAN, OS, NFFT, OVERLAP, "tukey", deripple_taps=h, dtype=torch.complex128, device=dev)
+    c64 = ana(x64)
+    y64 = inv(c64)
+    ms_a = _time_cuda(lambda: ana(x64, out=c64), 5)
+    ms_i = _time_cuda(lambda: inv(c64, out=y64), 5)
+    by = (x64.numel() + 2 * c64.numel() + y64.numel()) * 16
+    res["cfg2_fp64_mode"] = {"workload": "the bench workload in complex128 (generic kernels), 2 pol x 2^22",
+                             "ms_analysis": ms_a, "ms_inversion": ms_i, "value": 2 * n / (ms_a + ms_i) / 1e3, "unit": UNIT,
+                             "roofline": {"bound": "hbm", "achieved": by / ((ms_a + ms_i) * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                                          "frac": by / ((ms_a + ms_i) * 1e-3) / 1e9 / peak}}
+    del x64, c64, y64, ana, inv
+    torch.cuda.empty_cache()
     # ---- cfg5: batched purity sweep, impulse / tone / comb thirds, 147 456-sample vectors -------------------
     from ska_pst_dsp_model_b200.batch import BatchPurity
     vb = 128
