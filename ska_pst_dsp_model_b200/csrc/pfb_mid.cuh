@@ -446,14 +446,15 @@ __global__ void __launch_bounds__(2 * kPhArms * NU + 32, 2)
     // group gA - 1 was last touched by this warp one step ago: release it (every group exactly once)
     if (lane == 0 && gA >= 1) low::mbar_arrive(&empty[sA == 0 ? kPhGroups - 1 : sA - 1]);
     if (vv >= vskip && vv < kmax) {
-      float ax0 = 0, ay0 = 0, ax1 = 0, ay1 = 0;
+      // packed fp32x2 FMA with a scalar tap (FFMA2): 5 register reads per 2 MACs instead of 6
+      float2 a0 = make_float2(0.f, 0.f), a1 = make_float2(0.f, 0.f);
 #pragma unroll
       for (int m = 0; m < P; ++m) {
         const C x = w[(DE * sidx + m) % W];
-        if (m & 1) { ax1 += tap[m] * x.x; ay1 += tap[m] * x.y; }
-        else { ax0 += tap[m] * x.x; ay0 += tap[m] * x.y; }
+        if (m & 1) a1 = __ffma2_rn(make_float2(tap[m], tap[m]), make_float2(x.x, x.y), a1);
+        else a0 = __ffma2_rn(make_float2(tap[m], tap[m]), make_float2(x.x, x.y), a0);
       }
-      *yo = mk<float>(ax0 + ax1, ay0 + ay1);
+      *yo = mk<float>(a0.x + a1.x, a0.y + a1.y);
     }
     yo += ystride;
     ++gA;
