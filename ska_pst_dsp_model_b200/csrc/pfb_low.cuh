@@ -107,6 +107,26 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t
                : "memory");
 }
 
+// exp(-2 pi i k / 64) for the looped 64-point FFT passes of K1 (indexed by a warp-uniform loop counter: LDC / uniform
+// datapath, no register or shared-memory cost)
+__constant__ float2 kW64[64] = {
+    {1.0f, 0.0f}, {0.9951847266721969f, -0.0980171403295606f}, {0.9807852804032304f, -0.19509032201612825f}, {0.9569403357322088f, -0.29028467725446233f},
+    {0.9238795325112867f, -0.3826834323650898f}, {0.881921264348355f, -0.47139673682599764f}, {0.8314696123025452f, -0.5555702330196022f}, {0.773010453362737f, -0.6343932841636455f},
+    {0.7071067811865476f, -0.7071067811865475f}, {0.6343932841636455f, -0.773010453362737f}, {0.5555702330196023f, -0.8314696123025452f}, {0.4713967368259978f, -0.8819212643483549f},
+    {0.38268343236508984f, -0.9238795325112867f}, {0.29028467725446233f, -0.9569403357322089f}, {0.19509032201612833f, -0.9807852804032304f}, {0.09801714032956077f, -0.9951847266721968f},
+    {0.0f, -1.0f}, {-0.09801714032956065f, -0.9951847266721969f}, {-0.1950903220161282f, -0.9807852804032304f}, {-0.29028467725446216f, -0.9569403357322089f},
+    {-0.3826834323650897f, -0.9238795325112867f}, {-0.4713967368259977f, -0.881921264348355f}, {-0.555570233019602f, -0.8314696123025455f}, {-0.6343932841636454f, -0.7730104533627371f},
+    {-0.7071067811865475f, -0.7071067811865476f}, {-0.773010453362737f, -0.6343932841636455f}, {-0.8314696123025453f, -0.5555702330196022f}, {-0.8819212643483549f, -0.47139673682599786f},
+    {-0.9238795325112867f, -0.3826834323650899f}, {-0.9569403357322088f, -0.2902846772544624f}, {-0.9807852804032304f, -0.1950903220161286f}, {-0.9951847266721968f, -0.09801714032956083f},
+    {-1.0f, 0.0f}, {-0.9951847266721969f, 0.09801714032956059f}, {-0.9807852804032304f, 0.19509032201612836f}, {-0.9569403357322089f, 0.2902846772544621f},
+    {-0.9238795325112868f, 0.38268343236508967f}, {-0.881921264348355f, 0.47139673682599764f}, {-0.8314696123025455f, 0.555570233019602f}, {-0.7730104533627371f, 0.6343932841636453f},
+    {-0.7071067811865477f, 0.7071067811865475f}, {-0.6343932841636459f, 0.7730104533627367f}, {-0.5555702330196022f, 0.8314696123025452f}, {-0.47139673682599786f, 0.8819212643483549f},
+    {-0.38268343236509034f, 0.9238795325112865f}, {-0.29028467725446244f, 0.9569403357322088f}, {-0.19509032201612866f, 0.9807852804032303f}, {-0.09801714032956045f, 0.9951847266721969f},
+    {0.0f, 1.0f}, {0.09801714032956009f, 0.9951847266721969f}, {0.1950903220161283f, 0.9807852804032304f}, {0.29028467725446205f, 0.9569403357322089f},
+    {0.38268343236509f, 0.9238795325112866f}, {0.4713967368259976f, 0.881921264348355f}, {0.5555702330196018f, 0.8314696123025455f}, {0.6343932841636456f, 0.7730104533627369f},
+    {0.7071067811865474f, 0.7071067811865477f}, {0.7730104533627367f, 0.6343932841636459f}, {0.8314696123025452f, 0.5555702330196022f}, {0.8819212643483548f, 0.4713967368259979f},
+    {0.9238795325112865f, 0.3826834323650904f}, {0.9569403357322088f, 0.2902846772544625f}, {0.9807852804032303f, 0.19509032201612872f}, {0.9951847266721969f, 0.0980171403295605f}};
+
 // ===========================================================================
 // K1: analysis
 // ===========================================================================
@@ -131,6 +151,13 @@ struct AnaArgs {
   long long v_rows_cap;
 };
 
+#ifndef K1_FFT_UNROLL
+#define K1_FFT_UNROLL 2
+#endif
+#ifndef K1_FFT_UNROLL2
+#define K1_FFT_UNROLL2 K1_FFT_UNROLL
+#endif
+constexpr int kK1FftUnroll = K1_FFT_UNROLL, kK1FftUnroll2 = K1_FFT_UNROLL2;
 constexpr int kAnaStages = 3;
 constexpr int kTileBlocks = 4;                 // output blocks fed by one TMA tile
 constexpr int kTileSamples = kTileBlocks * 192;
@@ -294,20 +321,27 @@ __global__ void __launch_bounds__(64 * NPOL, NPOL == 2 ? 2 : 4) pfb_analysis_low
       // thread's private row in shared memory (the 48-sample window keeps the registers)
       const int o = tid & 3, tp = (tid >> 3) % NPOL, tj = 2 * (tid / (8 * NPOL)) + ((tid >> 2) & 1);   // row T = tid
       C* row = ex + (size_t)tid * kExStride;
-#pragma unroll
+      // both passes are LOOPS (unrolled by two), not straight-line code: the fully unrolled form made the loop body of
+      // this kernel 58 KB, beyond the 32 KB L1.5 instruction cache, and ncu charged 25 % of the stall samples to
+      // instruction fetch (no_inst); the inter-pass twiddles W64^(q oo) come from the constant bank, indexed by the
+      // warp-uniform loop counter
+#pragma unroll kK1FftUnroll
       for (int q = 0; q < 8; ++q) {
         C t[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) t[i] = row[q + 8 * i];
         Dft<8, -1, float>::run(t);
+        row[q] = t[0];
 #pragma unroll
-        for (int oo = 0; oo < 8; ++oo) row[q + 8 * oo] = mul_lit<64, -1>(t[oo], q * oo);
-        if (q & 1) asm volatile("" ::: "memory");   // keep at most two butterflies in flight (register budget)
+        for (int oo = 1; oo < 8; ++oo) {
+          const float2 w = kW64[q * oo];
+          row[q + 8 * oo] = mk<float>(t[oo].x * w.x - t[oo].y * w.y, t[oo].x * w.y + t[oo].y * w.x);
+        }
       }
       const long long kb = kA + 16ll * it + tj;
       C* op = a.out + ((a.kout0 + kb) * (FULL ? 256 : a.nchan_out)) * NPOL + tp + (FULL ? o * NPOL : 0);
       const bool live = kb < kend;
-#pragma unroll
+#pragma unroll kK1FftUnroll2
       for (int o1 = 0; o1 < 8; ++o1) {
         C t[8];
 #pragma unroll
@@ -323,7 +357,6 @@ __global__ void __launch_bounds__(64 * NPOL, NPOL == 2 ? 2 : 4) pfb_analysis_low
             if (live && ci < a.nchan_out) op[(long long)ci * NPOL] = t[o2];
           }
         }
-        if (o1 & 1) asm volatile("" ::: "memory");
       }
     }
     __syncthreads();

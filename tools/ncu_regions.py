@@ -10,8 +10,15 @@ import sys
 
 def main(rep):
     out = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv'], capture_output=True, text=True).stdout.splitlines()
-    rows = list(csv.reader(out[1:]))
-    hdr, rows = rows[0], rows[1:]
+    allrows = [r for r in csv.reader(out) if len(r) > 3]
+    # a report with several kernels repeats the header row: one table per kernel
+    starts = [i for i, r in enumerate(allrows) if 'Source' in r and '# Samples' in r]
+    for n, i0 in enumerate(starts):
+        i1 = starts[n + 1] if n + 1 < len(starts) else len(allrows)
+        regions(f"{rep} [kernel {n}]", allrows[i0], allrows[i0 + 1:i1])
+
+
+def regions(rep, hdr, rows):
     iS, iSamp, iEx = hdr.index('Source'), hdr.index('# Samples'), hdr.index('Instructions Executed')
     reasons = [(i, h) for i, h in enumerate(hdr) if h.startswith('stall_') and 'Not Issued' not in h]
     region, regs = 0, collections.OrderedDict()
