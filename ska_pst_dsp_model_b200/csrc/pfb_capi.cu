@@ -386,7 +386,7 @@ int fir_phases_launch<25, 7>(int nu, const AnalysisArgs& a, void* y, long long r
   constexpr size_t smem = mid::fir_phases_smem<25, 7>();
   cudaError_t e = cudaFuncSetAttribute(mid::pfb_fir_phases<25, 7, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
-  mid::pfb_fir_phases<25, 7, 8><<<dim3((unsigned)gx, (unsigned)nseg), 2 * mid::kPhArms * 8 + 32, smem, st>>>(f, tm);
+  mid::pfb_fir_phases<25, 7, 8><<<dim3((unsigned)gx, (unsigned)nseg), 2 * mid::kPhArms * 8, smem, st>>>(f, tm);
   return (int)cudaGetLastError();
 }
 

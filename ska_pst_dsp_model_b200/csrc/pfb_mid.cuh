@@ -340,8 +340,12 @@ __global__ void __launch_bounds__(256) pfb_spectrum24_step1(const SpecArgs a) {
 // window elements per step from there.  Taps and the circular register window are as in pfb_fir_slide.
 // Requires the window start of block 0 to fall on a multiple of N samples.
 // ---------------------------------------------------------------------------
-constexpr int kPhArms = 16;                            // sample arms per CTA (x 2 pols x nu phases = 256 compute threads)
-constexpr int kPhGroups = 9;                           // ring depth in row groups
+#ifndef PFB_PH_ARMS
+#define PFB_PH_ARMS 16
+#endif
+constexpr int kPhArms = PFB_PH_ARMS;                   // sample arms per CTA (x 2 pols x nu phases compute threads)
+constexpr int kPhGroups = 12;                          // ring depth in row groups
+constexpr int kPhLag = 3;                              // a group is refilled kPhLag steps after thread 0 released it
 
 struct FirPhasesArgs {
   void* y;               // [k][slot][2]
@@ -361,7 +365,7 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, in
 }
 
 template <int P, int DE, int NU>
-__global__ void __launch_bounds__(2 * kPhArms * NU + 32, 2)
+__global__ void __launch_bounds__(2 * kPhArms * NU, kPhArms <= 16 ? 2 : 1)
     pfb_fir_phases(const FirPhasesArgs a, const __grid_constant__ CUtensorMap in_map) {
   static_assert(DE < P, "long filters only");
   constexpr int NEW0 = P - DE;
@@ -394,19 +398,23 @@ __global__ void __launch_bounds__(2 * kPhArms * NU + 32, 2)
   const long long g0 = v0 + NEW0 / DE;
   const long long ngroups = ((NU - 1) + (long long)DE * (i_end - 1 - v0) + NEW0 % DE + DE - 1) / DE + 1;
 
-  if (warp == NWARP) {
-    if (lane != 0) return;
-    for (long long gi = 0; gi < ngroups; ++gi) {
-      const int sl = (int)(gi % kPhGroups);
-      if (gi >= kPhGroups) low::mbar_wait(&empty[sl], (uint32_t)((gi / kPhGroups - 1) & 1));
-      // slot 0 is written twice (also behind the last slot) so that a thread's DE consecutive rows never wrap
-      low::mbar_expect_tx(&full[sl], sl == 0 ? 2 * kGroupBytes : kGroupBytes);
-      tma_load_2d(ring + sl * DE * kRowC, &in_map, a0 * 4, (int)(a.row0 + (g0 + gi) * DE), &full[sl]);
-      if (sl == 0)
-        tma_load_2d(ring + kPhGroups * DE * kRowC, &in_map, a0 * 4, (int)(a.row0 + (g0 + gi) * DE), &full[sl]);
-    }
-    return;
-  }
+  // Loads are issued by thread 0 from inside its own step loop (no producer warp: 256 threads leave 128 registers per
+  // thread, the 288-thread form was capped at 96 and spilled): group gN goes into the slot of group gN - G, which every
+  // warp released kPhLag - 1 steps before thread 0 asks for it, so thread 0 only blocks when a warp lags that far.
+  int gN = 0, sN = 0;                                             // next group to issue, its slot
+  uint32_t parN = 1;                                              // parity of the slot's previous release (first lap: none)
+  auto issue_next = [&]() {
+    if (gN >= kPhGroups) low::mbar_wait(&empty[sN], parN);
+    low::mbar_expect_tx(&full[sN], sN == 0 ? 2 * kGroupBytes : kGroupBytes);
+    tma_load_2d(ring + sN * DE * kRowC, &in_map, a0 * 4, (int)(a.row0 + (g0 + gN) * DE), &full[sN]);
+    // slot 0 is written twice (also behind the last slot) so that a thread's DE consecutive rows never wrap
+    if (sN == 0) tma_load_2d(ring + kPhGroups * DE * kRowC, &in_map, a0 * 4, (int)(a.row0 + (g0 + gN) * DE), &full[sN]);
+    ++gN;
+    if (++sN == kPhGroups) { sN = 0; parN ^= 1u; }
+  };
+  const int ngroups_i = (int)ngroups;
+  if (tid == 0)
+    while (gN < kPhGroups - kPhLag && gN < ngroups_i) issue_next();
 
   const int k0 = tid / (2 * kPhArms);                             // block phase
   const int al = (tid % (2 * kPhArms)) >> 1, pol = tid & 1;                  // sample arm inside the group, polarisation
@@ -428,24 +436,81 @@ __global__ void __launch_bounds__(2 * kPhArms * NU + 32, 2)
   const int kmax = (int)min((long long)nv, (a.nblocks - k0 + a.nu - 1) / a.nu - v0);   // steps that produce a block
   yo += v0 * ystride;
   // the DE new rows of a step start r0 rows into group gA and gA advances by exactly one group per step, so the
-  // ring position, the two barrier slots and their parities are carried incrementally (no divisions in the loop)
+  // ring position, the barrier addresses and their parities are carried incrementally as shared-memory byte
+  // addresses (round 2, ncu r2y: with the positions recomputed per step only 20 % of the executed instructions were
+  // FIR arithmetic)
   const int q0 = s + NEW0 % DE;
-  int gA = q0 / DE;                                               // relative group of the first new row
-  const int r0 = q0 - gA * DE;
-  int sA = gA % kPhGroups;
-  uint32_t parA = (uint32_t)((gA / kPhGroups) & 1);
-  auto step = [&](auto sidx_c, int vv) {
+  const int gA0 = q0 / DE;                                        // relative group of the first new row
+  const int r0 = q0 - gA0 * DE;
+  int sA = gA0 % kPhGroups;
+  uint32_t parA = (uint32_t)((gA0 / kPhGroups) & 1);
+  constexpr uint32_t kGroupStride = DE * kRowC * sizeof(C);
+  const uint32_t full0 = low::smem_u32(full), empty0 = low::smem_u32(empty);
+  const uint32_t row_base = low::smem_u32(myring) + (uint32_t)r0 * kRowC * sizeof(C);
+  uint32_t offA = (uint32_t)sA * kGroupStride;                     // byte offset of group sA in the ring
+  bool release = gA0 >= 1;                                        // group gA - 1 exists (false at most on the first step)
+  const bool lane0 = lane == 0;
+  auto wait_addr = [](uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAITA_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONEA_%=;\n"
+        "bra WAITA_%=;\n"
+        "DONEA_%=:\n"
+        "}\n" ::"r"(bar), "r"(parity)
+        : "memory");
+  };
+  // One barrier per step, probed a whole FIR ahead: a step needs groups gA and (r0 != 0) gA + 1; every group before the
+  // LAST one it needs was already waited for by the previous step, so the step only has to see group
+  // gL = gA + (r0 != 0), and the (non-blocking) probe of the next step's gL is issued before this step's FIR, whose
+  // FFMA2 chain hides the probe's latency (ncu r2y2: the two back-to-back try_waits at the top of a step collected twice
+  // the stall samples of its 25 FFMA2s although they never had to spin)
+  auto probe = [](uint32_t bar, uint32_t parity) -> bool {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+  };
+  int sL = sA;                                                    // slot / parity of the last group the NEXT step needs
+  uint32_t parL = parA;
+  if (r0 != 0) {
+    wait_addr(full0 + 8u * (uint32_t)sA, parA);                   // group gA0 of the first step
+    if (++sL == kPhGroups) { sL = 0; parL ^= 1u; }
+  }
+  bool okL = false;
+  // MAIN: every step of the rotation produces a block and releases a group (no predicates)
+  auto step = [&](auto sidx_c, auto main_c, int vv) {
     constexpr int sidx = decltype(sidx_c)::value;
-    const int sB = sA + 1 == kPhGroups ? 0 : sA + 1;
-    low::mbar_wait(&full[sA], parA);
-    if (r0 != 0) low::mbar_wait(&full[sB], sB == 0 ? parA ^ 1u : parA);
-    const C* pr = myring + (sA * DE + r0) * kRowC;                // rows pr[0 .. DE): slot 0 is mirrored behind slot G - 1
+    constexpr bool MAIN = decltype(main_c)::value;
+    const bool last = sA + 1 == kPhGroups;
+    if (!okL) wait_addr(full0 + 8u * (uint32_t)sL, parL);
+    if (++sL == kPhGroups) { sL = 0; parL ^= 1u; }
+    okL = probe(full0 + 8u * (uint32_t)sL, parL);                 // next step's barrier, consumed after this step's FIR
+    const uint32_t pr = row_base + offA;                          // rows pr[0 .. DE): slot 0 is mirrored behind slot G - 1
 #pragma unroll
-    for (int m = 0; m < DE; ++m) w[(DE * sidx + NEW0 + m) % W] = pr[m * kRowC];
+    for (int m = 0; m < DE; ++m) {
+      float2 v;
+      asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(pr + (uint32_t)(m * kRowC * sizeof(C))));
+      w[(DE * sidx + NEW0 + m) % W] = mk<float>(v.x, v.y);
+    }
     __syncwarp();
     // group gA - 1 was last touched by this warp one step ago: release it (every group exactly once)
-    if (lane == 0 && gA >= 1) low::mbar_arrive(&empty[sA == 0 ? kPhGroups - 1 : sA - 1]);
-    if (vv >= vskip && vv < kmax) {
+    if (lane0 && (MAIN || release)) {
+      const uint32_t eb = empty0 + 8u * (uint32_t)(sA == 0 ? kPhGroups - 1 : sA - 1);
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(eb) : "memory");
+    }
+    release = true;
+    if (tid == 0 && gN < ngroups_i) issue_next();
+    if (MAIN || (vv >= vskip && vv < kmax)) {
       // packed fp32x2 FMA with a scalar tap (FFMA2): 5 register reads per 2 MACs instead of 6
       float2 a0 = make_float2(0.f, 0.f), a1 = make_float2(0.f, 0.f);
 #pragma unroll
@@ -457,20 +522,37 @@ __global__ void __launch_bounds__(2 * kPhArms * NU + 32, 2)
       *yo = mk<float>(a0.x + a1.x, a0.y + a1.y);
     }
     yo += ystride;
-    ++gA;
-    if (++sA == kPhGroups) { sA = 0; parA ^= 1u; }
+    if (last) { sA = 0; offA = 0; parA ^= 1u; }
+    else { ++sA; offA += kGroupStride; }
   };
   static_assert(PER == 4, "the unrolled step sequence below is written for a 4-step rotation");
+  const std::integral_constant<bool, false> edge;
+  const std::integral_constant<bool, true> mainc;
   int v = 0;
-  for (; v + PER <= nv; v += PER) {                               // whole rotations: straight-line code
-    step(std::integral_constant<int, 0>(), v);
-    step(std::integral_constant<int, 1>(), v + 1);
-    step(std::integral_constant<int, 2>(), v + 2);
-    step(std::integral_constant<int, 3>(), v + 3);
+  if (nv >= PER) {                                                // first rotation: window fill, predicates
+    step(std::integral_constant<int, 0>(), edge, 0);
+    step(std::integral_constant<int, 1>(), edge, 1);
+    step(std::integral_constant<int, 2>(), edge, 2);
+    step(std::integral_constant<int, 3>(), edge, 3);
+    v = PER;
+#pragma unroll 1
+    for (; v + PER <= kmax; v += PER) {                           // whole producing rotations: straight-line code
+      step(std::integral_constant<int, 0>(), mainc, v);
+      step(std::integral_constant<int, 1>(), mainc, v + 1);
+      step(std::integral_constant<int, 2>(), mainc, v + 2);
+      step(std::integral_constant<int, 3>(), mainc, v + 3);
+    }
   }
-  if (v < nv) step(std::integral_constant<int, 0>(), v);
-  if (v + 1 < nv) step(std::integral_constant<int, 1>(), v + 1);
-  if (v + 2 < nv) step(std::integral_constant<int, 2>(), v + 2);
+#pragma unroll 1
+  for (; v + PER <= nv; v += PER) {                               // tail rotations (blocks beyond the last one: consume only)
+    step(std::integral_constant<int, 0>(), edge, v);
+    step(std::integral_constant<int, 1>(), edge, v + 1);
+    step(std::integral_constant<int, 2>(), edge, v + 2);
+    step(std::integral_constant<int, 3>(), edge, v + 3);
+  }
+  if (v < nv) step(std::integral_constant<int, 0>(), edge, v);
+  if (v + 1 < nv) step(std::integral_constant<int, 1>(), edge, v + 1);
+  if (v + 2 < nv) step(std::integral_constant<int, 2>(), edge, v + 2);
 }
 
 template <int P, int DE> constexpr size_t fir_phases_smem() {
