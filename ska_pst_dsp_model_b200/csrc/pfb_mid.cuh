@@ -47,6 +47,12 @@ __global__ void __launch_bounds__(256, 2) pfb_rowfft4096(const RowFftArgs a) {
     {
       // pass A: n = t + 256 i  ->  o1 = k mod 16
       const float4* p = in + r * 4096;
+      if (r + gridDim.x < a.nrows) {
+        // the CTA's next row into L2 while this one is transformed (the loads of pass A are the kernel's longest stall)
+        const char* nx = reinterpret_cast<const char*>(in + (r + gridDim.x) * 4096) + t * 256;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(nx));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + 128));
+      }
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
         const int n = t + 256 * i;
