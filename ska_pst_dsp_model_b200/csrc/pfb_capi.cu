@@ -1157,6 +1157,8 @@ static int roundtrip_run(pfb_analysis_plan* ap, pfb_inverse_plan* ip, const void
   const long long vec_rows = nvec > 1 ? vec_samples / ap->S : nb_total;
   const long long rows_cap = nvec > 1 ? (long long)nvec * vec_rows : nb_total;
   const size_t need = (size_t)rows_cap * 256 * 16;
+  if (need >= ((size_t)1 << 32))
+    return fail(PFB_ERR_UNSUPPORTED, "fused round trip: the intermediate (%zu bytes) must stay below 4 GiB (32-bit offsets in the analysis kernel)", need);
   if ((long long)need > ip->scratch_bytes)
     return fail(PFB_ERR_UNSUPPORTED, "fused round trip: %zu bytes of scratch exceed the plan's cap (pfb_inverse_set_scratch_bytes)", need);
   if (need > ip->scratch_cap) {

@@ -248,6 +248,16 @@ __global__ void __launch_bounds__(64 * NPOL, NPOL == 2 ? 2 : 4) pfb_analysis_low
     }
   }
 
+  // fused emit: byte offsets of (group of t1 = r + 64 i, row of block kA + 16 it) in the grouped scratch (< 4 GiB,
+  // checked by the host)
+  uint32_t voff[4] = {0u, 0u, 0u, 0u};
+  const int vrow7 = (int)((a.kout0 + kA) & 7);
+  const int nloc = (int)(kend - kA);
+  if (EMIT > 0) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      voff[i] = (uint32_t)((((long long)((r >> 3) + 8 * i) * a.v_rows_cap + a.kout0 + kA) << 7) + pol * 8);
+  }
   for (int it = 0; it < niter; ++it) {
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
@@ -291,14 +301,14 @@ __global__ void __launch_bounds__(64 * NPOL, NPOL == 2 ? 2 : 4) pfb_analysis_low
 #pragma unroll
       for (int i = 0; i < 4; ++i) z[i] = acc[(i + j) & 3];
       if (EMIT > 0) {
-        // v[row][t1 = r + 64 i][pol] = N * z[i]: 16 consecutive r of a warp fill two whole 128-byte group rows
-        const long long row = a.kout0 + kA + 16ll * it + j;
-        if (kA + 16ll * it + j < kend) {
+        // v[row][t1 = r + 64 i][pol] = N * z[i] at grouped_unit(row, t1): 16 consecutive r of a warp fill two whole
+        // 128-byte group rows.  32-bit byte offsets from the (uniform) scratch base, carried per iteration; the row's
+        // swizzle (row & 7) depends on j only because an iteration advances 16 rows
+        if (16 * it + j < nloc) {
+          const uint32_t swz = (uint32_t)(((r & 7) ^ ((vrow7 + j) & 7)) << 4) + (uint32_t)(j * 128);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const long long u = grouped_unit(a.v_rows_cap, row, r + 64 * i);
-            *reinterpret_cast<C*>(a.v + u * 16 + pol * 8) = mk<float>(256.f * z[i].x, 256.f * z[i].y);
-          }
+          for (int i = 0; i < 4; ++i)
+            *reinterpret_cast<C*>(a.v + (size_t)(voff[i] + swz)) = mk<float>(256.f * z[i].x, 256.f * z[i].y);
         }
       }
       if (EMIT == 2) continue;
@@ -313,6 +323,10 @@ __global__ void __launch_bounds__(64 * NPOL, NPOL == 2 ? 2 : 4) pfb_analysis_low
 #pragma unroll
       for (int o = 0; o < 4; ++o)
         ex[(size_t)((((j >> 1) * NPOL + pol) * 8 + (j & 1) * 4) + o) * kExStride + r] = z[o];
+    }
+    if (EMIT > 0) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) voff[i] += 16u * 128u;
     }
     if (EMIT == 2) continue;
     __syncthreads();
