@@ -1262,6 +1262,14 @@ int pfb_generate_test_vectors(int kind, void* out_dev, long long n, int nvec, in
   long long gx = kind == 0 ? (n + 255) / 256 : (n + kGenSpan - 1) / kGenSpan;   // tones / combs: one CTA per 65 536-sample span
   const long long cap = nvec >= 148 ? 8 : 148 * 4;
   if (gx > cap) gx = cap;
+  if (dtype == PFB_DTYPE_C64 && group == 2 && nvec % 2 == 0 && group_stride % 2 == 0 && (uintptr_t)out_dev % 16 == 0) {
+    // both vectors of a [n][2] series from one CTA column: whole 16-byte elements
+    long long gp = kind == 0 ? (n + 255) / 256 : (n + kPairSpan - 1) / kPairSpan;
+    const long long capp = nvec >= 296 ? 8 : 148 * 8;
+    if (gp > capp) gp = capp;
+    pfb_generate_pairs_kernel<<<dim3((unsigned)gp, (unsigned)(nvec / 2)), 256, 0, st>>>(a);
+    return check_launch("pfb_generate_pairs_kernel");
+  }
   const dim3 grid((unsigned)gx, (unsigned)nvec);
   if (dtype == PFB_DTYPE_C64) pfb_generate_batch_kernel<float><<<grid, 256, 0, st>>>(a);
   else if (dtype == PFB_DTYPE_C128) pfb_generate_batch_kernel<double><<<grid, 256, 0, st>>>(a);

@@ -139,6 +139,68 @@ __global__ void __launch_bounds__(256) pfb_generate_batch_kernel(const GenBatchA
   }
 }
 
+// Pair form (complex64, group == 2): one CTA column generates BOTH vectors that share a [n][2] series and writes whole
+// 16-byte elements; the one-vector kernel above writes 8 of every 16 bytes, i.e. half of every 32-byte sector.
+constexpr int kPairSpan = 16384;   // samples per CTA pass of the pair generator (64 + 256 table entries per vector)
+__global__ void __launch_bounds__(256) pfb_generate_pairs_kernel(const GenBatchArgs a) {
+  __shared__ double comb_r[32], comb_i[32];
+  __shared__ float2 tabA[2][kPairSpan / 256], tabB[2][256];
+  const int pr = blockIdx.y;
+  float4* out = reinterpret_cast<float4*>(reinterpret_cast<Cx<float>*>(a.out) + (long long)pr * a.group_stride);
+  double p0[2], p1[2], p2[2];
+#pragma unroll
+  for (int s = 0; s < 2; ++s) {
+    p0[s] = a.params[3 * (2 * pr + s)];
+    p1[s] = a.params[3 * (2 * pr + s) + 1];
+    p2[s] = a.params[3 * (2 * pr + s) + 2];
+  }
+  if (a.kind == 0) {
+    const long long o0 = (long long)p0[0], w0 = (long long)p1[0], o1 = (long long)p0[1], w1 = (long long)p1[1];
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < a.n; t += (long long)gridDim.x * blockDim.x)
+      out[t] = make_float4((t >= o0 && t < o0 + w0) ? 1.f : 0.f, 0.f, (t >= o1 && t < o1 + w1) ? 1.f : 0.f, 0.f);
+    return;
+  }
+  if (a.kind == 2) {
+    if (threadIdx.x < 32) comb_table(comb_r, comb_i);
+    __syncthreads();
+  }
+  double f[2];
+#pragma unroll
+  for (int s = 0; s < 2; ++s)
+    f[s] = a.kind == 1 ? (p0[s] + p2[s]) / (double)a.n : -0.5 + 1.0 / 128.0 + p2[s] + p0[s] / (double)a.n;
+  for (long long t0 = (long long)blockIdx.x * kPairSpan; t0 < a.n; t0 += (long long)gridDim.x * kPairSpan) {
+    __syncthreads();
+    {
+      const int i = threadIdx.x;
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        double cyc = f[s] * (double)(t0 + 256ll * i);
+        double sn, cs;
+        if (i < kPairSpan / 256) {
+          sincos(2.0 * 3.14159265358979323846 * (cyc - floor(cyc)) + p1[s], &sn, &cs);
+          tabA[s][i] = make_float2((float)cs, (float)sn);
+        }
+        cyc = f[s] * (double)i;
+        sincos(2.0 * 3.14159265358979323846 * (cyc - floor(cyc)), &sn, &cs);
+        if (a.kind == 2) {
+          const int m = (int)((t0 + i) & 31);              // t0 is a multiple of 256: (t0 + 256 h + l) mod 32 = l mod 32
+          const double br = cs * comb_r[m] - sn * comb_i[m], bi = cs * comb_i[m] + sn * comb_r[m];
+          cs = br;
+          sn = bi;
+        }
+        tabB[s][i] = make_float2((float)cs, (float)sn);
+      }
+    }
+    __syncthreads();
+    const long long span = min((long long)kPairSpan, a.n - t0);
+    for (long long d = threadIdx.x; d < span; d += blockDim.x) {
+      const float2 A0 = tabA[0][d >> 8], B0 = tabB[0][d & 255], A1 = tabA[1][d >> 8], B1 = tabB[1][d & 255];
+      out[t0 + d] = make_float4(A0.x * B0.x - A0.y * B0.y, A0.x * B0.y + A0.y * B0.x, A1.x * B1.x - A1.y * B1.y,
+                                A1.x * B1.y + A1.y * B1.x);
+    }
+  }
+}
+
 struct MetricsArgs {
   const void* a;        // reference series (may be null), complex, element stride `stride`
   const void* b;        // series under test
