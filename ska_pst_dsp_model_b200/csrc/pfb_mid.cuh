@@ -158,7 +158,10 @@ inline int rowfft4096_launch(const RowFftArgs& a, cudaStream_t st) {
 //   x W448^(o m) -> exchange -> lane m < 14 runs one radix-32 inverse: y[m + 14 j], kept j in [8, 24).
 // One CTA = 16 columns (8 t1 x 2 pol) x one overlap-save block; weights come straight from the 14.7 MB table
 // (L2-resident, every CTA of a column group re-reads the same 28 KB).
-constexpr int kMidCols = 16;
+#ifndef PFB_MID_COLS
+#define PFB_MID_COLS 16
+#endif
+constexpr int kMidCols = PFB_MID_COLS;
 constexpr int kMidStrideA = 32 * 17 + 1;     // [o (32)][q (16)] padded: odd pitch per column
 constexpr int kMidStrideB = 14 * 33 + 1;     // [m (14)][o (32)]
 
@@ -179,7 +182,7 @@ constexpr size_t mid_res_smem_bytes() {
 // UNITY_MID: the temporal taper is exactly 1 on [ov, Nf - ov) (Tukey, top-hat interior, no window): only the 16 edge
 // samples of a lane are scaled.
 template <bool UNITY_MID>
-__global__ void __launch_bounds__(16 * kMidCols, 2) pfb_resample_mid(const MidResArgs a) {
+__global__ void __launch_bounds__(16 * kMidCols, 512 / (16 * kMidCols)) pfb_resample_mid(const MidResArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   C* ex = reinterpret_cast<C*>(smem_raw);              // [COLS][kMidStrideA], reused for the second exchange
   C* t1s = ex + kMidCols * kMidStrideA;                // [32 o][16 q]  exp(-2 pi i q o / 512)
@@ -210,6 +213,11 @@ __global__ void __launch_bounds__(16 * kMidCols, 2) pfb_resample_mid(const MidRe
   // and come from L2 (the register file has no room for a 16-element carry next to the 32-point butterflies)
   for (long long n = n_begin; n < n_end; ++n) {
   const C* vcol = a.v + (long long)t1_0 * 2 + c + (n * 256 + q) * rowlen;
+  if (n + 1 < n_end) {
+    // the 256 rows the NEXT block adds (one 128-byte segment per thread) into L2 while this block is transformed
+    const C* nx = a.v + (long long)t1_0 * 2 + ((n + 1) * 256 + 256 + tid % 256) * rowlen;
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(nx));
+  }
   C x[32];
   // phase 1: lane q holds tau = q + 16 i
 #pragma unroll
