@@ -111,8 +111,8 @@ int pfb_inverse_execute_batched(pfb_inverse_plan* plan, const void* in_dev, void
  *      The inverse DFT across channels of a channelized block equals N x the rotated polyphase arm sums the analysis
  *      kernel holds before its FFT, so the analysis writes the inversion's intermediate directly and the channel-IDFT
  *      kernel is not run.  chan_dev may be NULL (the channelized block is not wanted: the analysis then skips its FFT
- *      stage as well).  SKA-Low dual-pol complex64 fast path only: PFB_ERR_UNSUPPORTED otherwise (call
- *      pfb_analysis_execute + pfb_inverse_execute instead).  NOT a replacement for the file-based drop-in:
+ *      stage as well).  SKA-Low dual-pol complex64 fast path only, intermediate (n_blocks x 4096 bytes) below 4 GiB:
+ *      PFB_ERR_UNSUPPORTED otherwise (call pfb_analysis_execute + pfb_inverse_execute instead).  NOT a replacement for the file-based drop-in:
  *      synthesize() reads channelized files and uses pfb_inverse_execute. */
 int pfb_roundtrip_execute(pfb_analysis_plan* aplan, pfb_inverse_plan* iplan, const void* in_dev, void* chan_dev,
                           void* out_dev, int npol, long long n_dat, void* stream);

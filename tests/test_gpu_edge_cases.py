@@ -187,3 +187,22 @@ def test_cfg1_tensor_core_form_matches_oracle(pst_taps, monkeypatch):
     e_mma = np.abs(mma - ref[0]).max() / np.abs(ref).max()
     print(f"cfg1 FIR error vs fp64 oracle: CUDA cores {e_base:.2e}, tensor cores (3xTF32) {e_mma:.2e}")
     assert e_base < 1e-5 and e_mma < 1e-5 and not np.array_equal(base, mma)
+
+
+@pytest.mark.parametrize("rows", [40, 85, 88, 95, 102, 131, 257, 1000])
+def test_mid_phase_sharing_fir_matches_generic_at_every_length(rows, monkeypatch):
+    """SKA-Mid shape (4096 ch, 8/7, 25 taps per arm): the phase-sharing FIR (pfb_fir_phases: thread-0 TMA ring, one
+    early-probed barrier per step, first / producing / tail rotations) against the generic kernels of the same library
+    (PFB_NO_MID, read at plan creation) for streams from 'too short for the fast kernel' through a few steps to several
+    CTA segments, with a ragged tail."""
+    import torch
+    from ska_pst_dsp_model_b200 import ops
+    rng = np.random.default_rng(rows)
+    h = rng.standard_normal(100353) / 300.0
+    x = torch.from_numpy(cn(rng, (4096 * rows + 1234, 2))).cuda()
+    fast = ops.AnalysisPlan(4096, "8/7", h, "polyphase_analysis_padded")(x).cpu().numpy()
+    monkeypatch.setenv("PFB_NO_MID", "1")
+    slow = ops.AnalysisPlan(4096, "8/7", h, "polyphase_analysis_padded")(x).cpu().numpy()
+    monkeypatch.delenv("PFB_NO_MID")
+    assert fast.shape == slow.shape and fast.shape[0] > 0
+    assert nerr(fast, slow) < 2e-6
