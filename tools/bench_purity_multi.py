@@ -21,6 +21,7 @@ VB = 128
 nvec = int(os.environ.get("NVEC", str(VB * 8 * 8)))   # per kind (impulse, tone, comb): whole chunks on 1..8 GPUs
 h = load_pst_taps(normalise=True)
 bp = BatchPurity("4/3", 256, 48, "tukey", True, 256, h, 3, vectors_per_batch=VB)
+bp.reserve(nvec // world + VB)                      # pinned staging for this rank's share
 bp.sweep(VB * world, 3, rank, world)                # warm-up: scratch sized, graphs for the chunk size captured
 torch.cuda.synchronize()
 if world > 1:
