@@ -704,6 +704,15 @@ constexpr int kWsStepRows = 160;                      // keep = Nf - 2 ov
 constexpr int kWsSlots = 2;
 constexpr int kWsColStride = 280;                     // per-pol exchange buffer pitch: 560 words = 16 (mod 32)
 constexpr int kWsOutRows = 120;                       // keep2
+#ifndef K3_TAPER_REGS
+#define K3_TAPER_REGS 1
+#endif
+#ifndef K3_TW1_REGS
+#define K3_TW1_REGS 6
+#endif
+#ifndef K3_TW2_REGS
+#define K3_TW2_REGS 0
+#endif
 
 struct WsArgs {
   const char* v;        // grouped scratch
@@ -819,6 +828,17 @@ __global__ void __launch_bounds__(32 * (kWsWarps + 1), 2)
   // byte offset of this lane's column inside a ring row: unit (t1l ^ (row & 7)), row & 7 == q & 7
   const int coloff = ((warp ^ (q & 7)) << 4) + (pol << 3);
 
+#if K3_TAPER_REGS
+  float tpr[6];                                       // the lane's six edge taper values: loop-invariant, kept in registers
+#pragma unroll
+  for (int i = 0; i < 6; ++i) tpr[i] = stp[q + 16 * (i < 3 ? i : i + 10)];
+#endif
+  C tw1r[K3_TW1_REGS > 0 ? K3_TW1_REGS : 1];          // first-exchange twiddles of o = 1 .. K3_TW1_REGS: loop-invariant per lane
+#pragma unroll
+  for (int o = 1; o <= K3_TW1_REGS; ++o) tw1r[o - 1] = t1s[o * 16 + q];
+  C tw2r[K3_TW2_REGS > 0 ? K3_TW2_REGS : 1];          // second-exchange twiddles of m = 1 .. K3_TW2_REGS (lane o = q)
+#pragma unroll
+  for (int m = 1; m <= K3_TW2_REGS; ++m) tw2r[m - 1] = t2s[m * 16 + q];
   C carry[6];
   {
     mbar_wait(&full[0], 0);
@@ -844,14 +864,22 @@ __global__ void __launch_bounds__(32 * (kWsWarps + 1), 2)
       if (lane == 0) mbar_arrive(&empty[k & 1]);
 #pragma unroll
       for (int i = 0; i < 6; ++i) carry[i] = x[i + 10];
+#if K3_TAPER_REGS
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        if (!UNITY_MID) x[i] = x[i] * stp[q + 16 * i];
+        else if (i < 3) x[i] = x[i] * tpr[i];
+        else if (i >= 13) x[i] = x[i] * tpr[i - 10];
+#else
 #pragma unroll
       for (int i = 0; i < 16; ++i)
         if (!UNITY_MID || i < 3 || i >= 13) x[i] = x[i] * stp[q + 16 * i];      // ov = 48 = 3 * 16
+#endif
       fft_reg<4, 4, -1>(x);
 #pragma unroll
       for (int o = 0; o < 16; ++o) {
         C v = x[slot<4, 4>(o)];
-        if (o) v = v * t1s[o * 16 + q];
+        if (o) v = v * (o <= K3_TW1_REGS ? tw1r[o - 1 < K3_TW1_REGS ? o - 1 : 0] : t1s[o * 16 + q]);
         ex[o * kQStride + q] = v;
       }
     }
@@ -875,7 +903,7 @@ __global__ void __launch_bounds__(32 * (kWsWarps + 1), 2)
 #pragma unroll
       for (int m = 0; m < 12; ++m) {
         C v = z[slot<3, 4>(m)];
-        if (m) v = v * t2s[m * 16 + o];
+        if (m) v = v * (m <= K3_TW2_REGS ? tw2r[m - 1 < K3_TW2_REGS ? m - 1 : 0] : t2s[m * 16 + o]);
         ex[m * kQStride + o] = v;
       }
     }
