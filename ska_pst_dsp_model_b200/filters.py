@@ -67,6 +67,76 @@ def design_pfb_fir_filter_two_stage(n_chan, os_nu, os_de, os_taps_per_chan=28, z
     return np.real(np.fft.fftshift(np.fft.ifft(hz)))
 
 
+def interpft(x, ny):
+    """Matlab's `interpft(x, ny)` for a real vector: resampling of the trigonometric interpolant through the FFT (zero
+    padding in the middle of the spectrum, the Nyquist bin of an even-length input split in two, scale ny/m); when
+    ny < m Matlab interpolates to the next multiple incr*ny > m and keeps every incr-th sample."""
+    x = np.asarray(x, dtype=np.float64)
+    m = x.size
+    incr = 1
+    if ny <= m:
+        incr = m // ny + 1
+        ny = incr * ny
+    a = np.fft.fft(x)
+    nyq = (m + 2) // 2                                   # ceil((m + 1) / 2)
+    b = np.concatenate([a[:nyq], np.zeros(ny - m, dtype=complex), a[nyq:]])
+    if m % 2 == 0:
+        b[nyq - 1] /= 2
+        b[nyq - 1 + ny - m] = b[nyq - 1]
+    y = np.real(np.fft.ifft(b)) * ny / m
+    return y[::incr]
+
+
+def maxflat_sym(order, wn):
+    """Symmetric (linear-phase) maximally flat FIR low-pass of even `order` whose magnitude passes 1/sqrt(2) nearest to
+    `wn` (units of Nyquist): Herrmann's closed form A(w) = cos^(2L)(w/2) * sum_{k<K} C(L-1+k, k) sin^(2k)(w/2) with L
+    zeros at z = -1 and K = order/2 + 1 - L degrees of flatness at w = 0 - the filter Matlab's `maxflat(n, 'sym', wn)`
+    designs (generate_MaxFlt.m:35).  Unpinned against Matlab (not available): L is the integer whose half-power
+    frequency is closest to wn."""
+    from math import comb
+    if order % 2:
+        raise ValueError("maxflat_sym: the order must be even")
+    M = order // 2
+
+    def response(L, w):
+        c2, s2 = np.cos(w / 2) ** 2, np.sin(w / 2) ** 2
+        return c2 ** L * sum(comb(L - 1 + k, k) * s2 ** k for k in range(M + 1 - L))
+
+    grid = np.linspace(0, np.pi, 8193)
+    best = None
+    for L in range(1, M + 1):
+        r = response(L, grid)
+        wc = grid[np.argmin(np.abs(r - np.sqrt(0.5)))] / np.pi
+        if best is None or abs(wc - wn) < best[0]:
+            best = (abs(wc - wn), L)
+    L = best[1]
+    n = order + 1
+    A = response(L, 2 * np.pi * np.arange(n) / n)        # a cosine polynomial of degree M: n samples determine it
+    h = np.real(np.fft.ifft(A))
+    return np.roll(h, M)                                 # centred: h[M] is the peak
+
+
+def generate_maxflat(nbuff, ntap, iterations=10):
+    """The maximally flat prototype of matlab/generate_MaxFlt.m:32-71 (J. Bunton): a 2*ntap-tap two-channel filter from
+    `maxflat`, ten fixed-point passes that push |H(f)|^2 + |H(f + pi)|^2 towards 1 (constant total power over the
+    channels for a monochromatic input), then trigonometric interpolation to nbuff*ntap taps.  Returns (W, residual)
+    with residual = max |1 - (|H|^2 + |H shifted|^2) / value at DC| of the 2*ntap-tap filter."""
+    n2 = 2 * ntap
+    imp = maxflat_sym(n2, 0.5 * n2 / (n2 + 1))
+    imp = interpft(imp, n2) * (n2 + 1) / n2
+    alt = np.cos(np.arange(n2) * np.pi)
+    resid = None
+    for _ in range(iterations + 1):
+        f, fh = np.fft.fft(imp), np.fft.fft(imp * alt)
+        e = np.real(f * np.conj(f) + fh * np.conj(fh))
+        e = 1.0 - e / e[0]
+        resid = float(np.abs(e).max())
+        if _ == iterations:
+            break
+        imp = imp + np.real(np.fft.fftshift(np.fft.ifft(e))) / 2.0
+    return interpft(imp, nbuff * ntap), resid
+
+
 _DESIGN_CACHE = {}
 
 

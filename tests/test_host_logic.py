@@ -234,3 +234,24 @@ def test_filter_designs_against_independent_least_squares(tmp_path):
     for ext in (".mat", ".txt", ".npy"):
         back = read_fir_filter_coeff(str(tmp_path / ("Prototype_FIR.2_stage.8-7.4096.100352" + ext)))
         assert np.array_equal(back, hm)
+
+
+def test_maxflat_prototype_design():
+    """generate_MaxFlt.m:32-71 restated (filters.generate_maxflat): the trigonometric resampler is exact on band-limited
+    series in both directions, the Herrmann filter is symmetric, monotone, has unit gain at DC, a zero at Nyquist and its
+    half-power point next to the requested frequency, and the ten passes drive the two-channel power sum to a constant."""
+    from ska_pst_dsp_model_b200.filters import generate_maxflat, interpft, maxflat_sym
+    k16, k64 = np.arange(16), np.arange(64)
+    assert np.abs(interpft(np.cos(2 * np.pi * 3 * k16 / 16 + 0.3), 64) - np.cos(2 * np.pi * 3 * k64 / 64 + 0.3)).max() < 1e-12
+    k25, k24 = np.arange(25), np.arange(24)
+    assert np.abs(interpft(np.cos(2 * np.pi * 2 * k25 / 25 + 0.1), 24) - np.cos(2 * np.pi * 2 * k24 / 24 + 0.1)).max() < 1e-12
+    h = maxflat_sym(24, 0.48)
+    assert h.size == 25 and np.allclose(h, h[::-1], atol=1e-15) and abs(h.sum() - 1) < 1e-12
+    assert abs(np.polyval(h, -1.0)) < 1e-12                                   # zero at z = -1
+    H = np.abs(np.fft.rfft(h, 4096))
+    assert np.all(np.diff(H) <= 1e-12)
+    assert abs(np.argmin(np.abs(H - np.sqrt(0.5))) / 2048 - 0.48) < 0.02
+    res = [generate_maxflat(32, 12, it)[1] for it in (0, 1, 3, 10)]
+    assert res[0] > 1e-2 and all(a > b for a, b in zip(res, res[1:])) and res[-1] < 1e-10
+    W, _ = generate_maxflat(32, 12)
+    assert W.shape == (32 * 12,) and np.isfinite(W).all()

@@ -7,6 +7,8 @@ git-ignores (config/Prototype_FIR.*.mat), as .mat (field `h`, plus n_chan / Fp /
                                                                weights [1, 15]
   two stage    : matlab/design_PFB_FIR_filter_two_stage.m:42-78 firls at 32x the band edges (0.998 Fs), then FFT-domain
                                                                zero stuffing to the full length (100 353 taps for Mid)
+  maxflat      : matlab/generate_MaxFlt.m:32-71                 symmetric maximally flat two-channel filter, ten passes towards
+                                                               constant total power, interpolated to channels x taps
 
     python tools/design_filters.py --out ska_pst_dsp_model_b200/data/designed            # all designs of test.config.json
     python tools/design_filters.py --design single_stage --channels 256 --os 4/3 --taps-per-chan 12 --out /tmp/f
@@ -61,6 +63,13 @@ def design(kind, channels, os_factor, taps_per_chan=None):
         h = design_pfb_fir_filter(channels, nu, de, taps_per_chan)
     elif kind == "two_stage":
         h = design_pfb_fir_filter_two_stage(channels, nu, de)
+    elif kind == "maxflat":
+        # matlab/generate_MaxFlt.m:32-71 (nbuff = channels, nTap = taps per channel): no band edges, the oversampling
+        # factor plays no part in the design
+        from ska_pst_dsp_model_b200.filters import generate_maxflat
+        h, resid = generate_maxflat(channels, taps_per_chan)
+        meta = {"n_chan": channels, "Fp": 0.0, "Fs": 0.0, "os_factor": f"{nu}/{de}", "design": kind,
+                "power_complementarity_residual": resid}
     else:
         raise ValueError(f"unknown design {kind!r}")
     return np.asarray(h, dtype=np.float64), meta
@@ -90,7 +99,7 @@ def write(h, meta, out_dir, stem):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", required=True)
-    ap.add_argument("--design", choices=["single_stage", "two_stage"])
+    ap.add_argument("--design", choices=["single_stage", "two_stage", "maxflat"])
     ap.add_argument("--channels", type=int)
     ap.add_argument("--os", dest="os_factor")
     ap.add_argument("--taps-per-chan", type=int, default=12)
