@@ -704,14 +704,16 @@ constexpr int kWsStepRows = 160;                      // keep = Nf - 2 ov
 constexpr int kWsSlots = 2;
 constexpr int kWsColStride = 280;                     // per-pol exchange buffer pitch: 560 words = 16 (mod 32)
 constexpr int kWsOutRows = 120;                       // keep2
+// Compile-time tuning knobs (tools/build_variants2.sh builds variants side by side; values below are the measured best):
+// loop-invariant per-lane table values kept in registers instead of re-read from shared memory every block
 #ifndef K3_TAPER_REGS
-#define K3_TAPER_REGS 1
+#define K3_TAPER_REGS 1      // the six edge taper values of a lane
 #endif
 #ifndef K3_TW1_REGS
-#define K3_TW1_REGS 6
+#define K3_TW1_REGS 6        // first-exchange twiddles o = 1..6 (8, 10: no further gain)
 #endif
 #ifndef K3_TW2_REGS
-#define K3_TW2_REGS 0
+#define K3_TW2_REGS 0        // second-exchange twiddles (4, 6: slightly slower)
 #endif
 
 struct WsArgs {
