@@ -149,3 +149,50 @@ def test_fused_round_trip_matches_oracle_and_two_plan_form(pst_taps):
     assert nerr(y_two.cpu().numpy(), y1.cpu().numpy()) < 2e-6
     with pytest.raises(PfbError):                                    # other shapes: not fused
         ops.round_trip(ops.AnalysisPlan(8, "8/7", h), ops.InversePlan(8, "8/7", 256, 48, "tukey"), xd[:, :1].contiguous())
+
+
+@pytest.mark.parametrize("kind", [0, 1, 2])
+def test_pair_generator_equals_one_vector_generator(kind):
+    """pfb_generate_test_vectors: the pair kernel (group == 2: both vectors of a [n][2] series from one CTA column,
+    16-byte stores) writes exactly what the one-vector kernel writes (group == 1, one vector after the other)."""
+    import torch
+    from ska_pst_dsp_model_b200 import lib as _l
+    n, nvec = 40000, 6
+    rng = np.random.default_rng(kind)
+    if kind == 0:
+        prm = np.stack([rng.integers(0, n, nvec), np.full(nvec, 3), np.zeros(nvec)], axis=1).astype(np.float64)
+    else:
+        prm = np.stack([rng.uniform(0, n / 2, nvec), rng.uniform(0, 1, nvec), np.full(nvec, 1.0 / 1024 if kind == 2 else 0.25)],
+                       axis=1)
+    dprm = torch.from_numpy(prm).cuda()
+    pairs = torch.zeros((nvec // 2, n, 2), dtype=torch.complex64, device="cuda")
+    singles = torch.zeros((nvec, n), dtype=torch.complex64, device="cuda")
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    _l.check(_l.lib.pfb_generate_test_vectors(kind, pairs.data_ptr(), n, nvec, 2, n * 2, _l.PFB_DTYPE_C64, dprm.data_ptr(), st))
+    _l.check(_l.lib.pfb_generate_test_vectors(kind, singles.data_ptr(), n, nvec, 1, n, _l.PFB_DTYPE_C64, dprm.data_ptr(), st))
+    torch.cuda.synchronize()
+    got = pairs.permute(0, 2, 1).reshape(nvec, n)
+    assert float((got - singles).abs().max()) <= 2e-7          # same factors; the span of the A/B tables differs
+    assert float(singles.abs().max()) > 0
+
+
+def test_async_sweep_equals_kind_by_kind_runs(pst_taps):
+    """BatchPurity.sweep enqueues all kinds before it builds any report (pinned staging, reserve()); the reports equal the
+    ones of the synchronous per-kind entry points."""
+    import torch
+    from ska_pst_dsp_model_b200.batch import BatchPurity
+    h = pst_taps / pst_taps.sum()
+    bp = BatchPurity("4/3", 256, 48, "tukey", True, 256, h, 3, vectors_per_batch=16)
+    bp.reserve(40)
+    rep = bp.sweep(40, 3)
+    offsets = np.linspace(1, bp.n_samples, 40).astype(int)
+    freqs = np.linspace(1, bp.block_size, 40).astype(int) * 3
+    shifts = np.linspace(0, bp.n_samples / 32.0, 40)
+    for got, ref in ((rep["test_time_domain_impulse"], bp.temporal(offsets)), (rep["test_complex_sinusoid"], bp.spectral(freqs)),
+                     (rep["test_frequency_comb"], bp.comb(shifts))):
+        assert len(got) == len(ref) == 40
+        for a, b in zip(got, ref):
+            assert a.keys() == b.keys()
+            for k in a:
+                assert a[k] == b[k] or abs(a[k] - b[k]) <= 1e-12 * max(1.0, abs(b[k]))
+    torch.cuda.synchronize()
